@@ -1,0 +1,260 @@
+/* nmpc_b200 -- C ABI of the batched DDP/iLQR and FMPC engines (libnmpc_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of isri-aist/NMPC.  The reference has no FFI of its
+ * own: its boundary is the C++ template API nmpc_ddp::DDPSolver<StateDim, InputDim>
+ * (nmpc_ddp/include/nmpc_ddp/DDPSolver.h:23-375) and nmpc_fmpc::FmpcSolver<StateDim, InputDim,
+ * IneqDim> (nmpc_fmpc/include/nmpc_fmpc/FmpcSolver.h:22-424).  Each entry point below names the
+ * reference member it stands in for; include/nmpc_ddp/DDPSolver.h and
+ * include/nmpc_fmpc/FmpcSolver.h re-create the template API on top of these calls.
+ *
+ * Conventions
+ *  - plain C types only; every function returns an nmpc_b200_status (0 = OK) and never throws;
+ *    nmpc_b200_last_error() returns the message of the last failure on the calling thread.
+ *  - all host- or device-side I/O arrays are instance-major ("one solver object after another"):
+ *      x0[B][NX], u[B][N][NU], x[B][N+1][NX], cost_list[B][N+1], k[B][N][NU],
+ *      K[B][N][NU*NX] (column-major NU x NX per step, like Eigen), trace[B][max_iter+1][9].
+ *    Inside the engine the batch index is the fastest-varying one.
+ *  - `on_device` != 0 means the pointers are device pointers on the handle's device; the call is
+ *    then asynchronous on `stream` (a cudaStream_t passed as void*, NULL = the handle's own stream).
+ *  - a handle is not re-entrant (like a DDPSolver object); distinct handles are independent.
+ *  - there is no CPU fallback: creation fails with NMPC_B200_ERR_NO_DEVICE when no CUDA device
+ *    is usable.
+ */
+#ifndef NMPC_B200_C_API_H
+#define NMPC_B200_C_API_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define NMPC_B200_VERSION 100
+
+  typedef enum
+  {
+    NMPC_B200_OK = 0,
+    NMPC_B200_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference (DDPSolver.hpp:41-45) */
+    NMPC_B200_ERR_RUNTIME = 2, /* std::runtime_error in the reference (DDPSolver.hpp:51-56, :393) */
+    NMPC_B200_ERR_UNKNOWN_MODEL = 3,
+    NMPC_B200_ERR_NO_DEVICE = 4,
+    NMPC_B200_ERR_CUDA = 5,
+    NMPC_B200_ERR_CAPACITY = 6,
+    NMPC_B200_ERR_UNSUPPORTED = 7
+  } nmpc_b200_status;
+
+  /** Message of the last error raised on this thread ("" if none). */
+  const char * nmpc_b200_last_error(void);
+  int nmpc_b200_version(void);
+  /** Number of usable CUDA devices (0 when the driver or a device is missing). */
+  int nmpc_b200_device_count(void);
+
+  /* ------------------------------------------------------------------ problem functors ---- */
+
+  /** Dimensions of a registered problem functor (stands in for DDPProblem::stateDim()/inputDim(),
+      DDPProblem.h:52-85, and FmpcProblem::ineqDim(), FmpcProblem.h:62-86).  `ng` is 0 for functors
+      without inequality constraints. */
+  int nmpc_b200_model_dims(const char * model, int * nx, int * nu, int * ng, int * n_params);
+  /** Default flat parameter vector of a registered functor (n_params doubles). */
+  int nmpc_b200_model_default_params(const char * model, double * params);
+  /** Number of registered functors and their names (for diagnostics). */
+  int nmpc_b200_model_count(void);
+  const char * nmpc_b200_model_name(int index);
+
+  /** Evaluate a functor ON THE DEVICE at `n` points (derivative checks, TestDDPCartPole.cpp:609-649).
+      Inputs (host): t[n], x[n][NX], u[n][NU].  Outputs (host, any may be NULL): x_next[n][NX],
+      running_cost[n], terminal_cost[n], Fx[n][NX*NX], Fu[n][NX*NU], Lx[n][NX], Lu[n][NU],
+      Lxx[n][NX*NX], Luu[n][NU*NU], Lxu[n][NX*NU], Vx[n][NX], Vxx[n][NX*NX], g[n][NG], C[n][NG*NX],
+      D[n][NG*NU]; matrices column-major. */
+  int nmpc_b200_model_eval(const char * model,
+                           const double * params,
+                           int n_params,
+                           int device,
+                           int n,
+                           const double * t,
+                           const double * x,
+                           const double * u,
+                           double * x_next,
+                           double * running_cost,
+                           double * terminal_cost,
+                           double * Fx,
+                           double * Fu,
+                           double * Lx,
+                           double * Lu,
+                           double * Lxx,
+                           double * Luu,
+                           double * Lxu,
+                           double * Vx,
+                           double * Vxx,
+                           double * g,
+                           double * C,
+                           double * D);
+
+  /* ----------------------------------------------------------------------------- DDP ---- */
+
+  /** Mirror of DDPSolver::Configuration (DDPSolver.h:47-110), same defaults.  print_level has no
+      meaning for a batch; use_state_eq_second_derivative is rejected exactly where the reference
+      throws (DDPSolver.hpp:391-414). */
+  typedef struct
+  {
+    int horizon_steps; /* 100 */
+    int max_iter; /* 500 */
+    int reg_type; /* 1: Quu + lambda I, 2: Vxx + lambda I */
+    int with_input_constraint; /* 0 */
+    int n_alpha; /* 11 */
+    int use_state_eq_second_derivative; /* 0; non-zero => NMPC_B200_ERR_RUNTIME at solve() */
+    double initial_lambda; /* 1e-4 */
+    double initial_dlambda; /* 1.0 */
+    double lambda_factor; /* 1.6 */
+    double lambda_min; /* 1e-6 */
+    double lambda_max; /* 1e10 */
+    double k_rel_norm_thre; /* 1e-4 */
+    double lambda_thre; /* 1e-5 */
+    double cost_update_ratio_thre; /* 0 */
+    double cost_update_thre; /* 1e-7 */
+    double alpha_list[16]; /* 10^linspace(0,-3,11) */
+  } nmpc_b200_ddp_config;
+
+  void nmpc_b200_ddp_config_default(nmpc_b200_ddp_config * cfg);
+
+  typedef struct nmpc_b200_ddp nmpc_b200_ddp; /* opaque: a batch of DDPSolver objects on one GPU */
+
+  /** DDPSolver::DDPSolver(problem) (DDPSolver.hpp:20-24) for `batch_capacity` instances that share one
+      problem functor and parameter set.  `device` is a CUDA ordinal. */
+  int nmpc_b200_ddp_create(const char * model,
+                           const double * params,
+                           int n_params,
+                           const nmpc_b200_ddp_config * cfg,
+                           int batch_capacity,
+                           int device,
+                           nmpc_b200_ddp ** out);
+  int nmpc_b200_ddp_destroy(nmpc_b200_ddp * h);
+
+  /** DDPSolver::config() (DDPSolver.h:258-267).  Changing horizon_steps or max_iter reallocates. */
+  int nmpc_b200_ddp_set_config(nmpc_b200_ddp * h, const nmpc_b200_ddp_config * cfg);
+  int nmpc_b200_ddp_get_config(const nmpc_b200_ddp * h, nmpc_b200_ddp_config * cfg);
+
+  /** DDPSolver::setInputLimitsFunc (DDPSolver.h:282-285) for limits constant over the horizon:
+      lower[NU], upper[NU] (host). */
+  int nmpc_b200_ddp_set_input_limits(nmpc_b200_ddp * h, const double * lower, const double * upper);
+
+  /** DDPSolver::solve(current_t, current_x, initial_u_list) (DDPSolver.hpp:27-141) for B <= capacity
+      independent instances: x0[B][NX], u_init[B][N][NU].  n_u_steps must equal horizon_steps
+      (else NMPC_B200_ERR_INVALID_ARGUMENT, as DDPSolver.hpp:41-45 throws). */
+  int nmpc_b200_ddp_solve(nmpc_b200_ddp * h,
+                          int B,
+                          double current_t,
+                          const double * x0,
+                          const double * u_init,
+                          int n_u_steps,
+                          int on_device,
+                          void * stream);
+
+  typedef enum
+  {
+    NMPC_B200_DDP_X = 0, /* controlData().x_list     double [B][N+1][NX] */
+    NMPC_B200_DDP_U = 1, /* controlData().u_list     double [B][N][NU] */
+    NMPC_B200_DDP_COST_LIST = 2, /* controlData().cost_list  double [B][N+1] */
+    NMPC_B200_DDP_K_FF = 3, /* k_list_                  double [B][N][NU] */
+    NMPC_B200_DDP_K_FB = 4, /* K_list_                  double [B][N][NU*NX] */
+    NMPC_B200_DDP_TRACE = 5, /* traceDataList()          double [B][max_iter+1][9]: iter cost lambda dlambda alpha
+                                k_rel_norm cost_update_actual cost_update_expected cost_update_ratio */
+    NMPC_B200_DDP_STATUS = 6, /* last procOnce retval     int [B]: 1 converged (solve() true), 0 max_iter, -1 failure */
+    NMPC_B200_DDP_ITERS = 7, /* traceDataList().back().iter  int [B] */
+    NMPC_B200_DDP_N_FORWARD = 8, /* forwardPass() calls      int [B] */
+    NMPC_B200_DDP_N_BACKWARD = 9, /* backwardPass() calls     int [B] */
+    NMPC_B200_DDP_COST = 10, /* cost_list.sum()          double [B] */
+    NMPC_B200_DDP_U0 = 11, /* u_list[0]                double [B][NU] */
+    NMPC_B200_DDP_N_TRACE = 12 /* traceDataList().size()   int [B] */
+  } nmpc_b200_ddp_field;
+
+  /** controlData()/traceDataList() accessors (DDPSolver.h:288-303): copies field `what` of the last
+      solve into dst (dst_bytes must be at least the field size for the last B). */
+  int nmpc_b200_ddp_get(nmpc_b200_ddp * h, int what, void * dst, size_t dst_bytes, int dst_on_device, void * stream);
+
+  /** Wait for the handle's pending work. */
+  int nmpc_b200_ddp_sync(nmpc_b200_ddp * h);
+
+  /** computationDuration() (DDPSolver.h:219-247, :300-303) measured with CUDA events on the solve
+      stream.  Enable before solve(); get() waits for the events.  ms[8] = {solve, setup (layout +
+      initial rollout), opt, derivative, backward, forward, copy_in, copy_out}; launches[4] = number
+      of launches of {rollout, derivative, backward, forward} kernels in the last solve. */
+  int nmpc_b200_ddp_enable_timing(nmpc_b200_ddp * h, int enable);
+  int nmpc_b200_ddp_get_durations(nmpc_b200_ddp * h, double * ms, int * launches);
+
+  /* ---------------------------------------------------------------------------- FMPC ---- */
+
+  /** Mirror of FmpcSolver::Configuration (FmpcSolver.h:58-89). */
+  typedef struct
+  {
+    int horizon_steps; /* 100 */
+    int max_iter; /* 10 */
+    int check_nan; /* 1 */
+    int init_complementary_variable; /* 0 */
+    int update_barrier_eps; /* 1 */
+    int break_if_llt_fails; /* 0 */
+    int enable_line_search; /* 0 */
+    int merit_const_scale_from_lagrange_multipliers; /* 0 */
+    double kkt_error_thre; /* 1e-4 */
+    double initial_barrier_eps; /* barrier_eps_ on entry (FmpcSolver.h:413-414): 1e-4 */
+  } nmpc_b200_fmpc_config;
+
+  void nmpc_b200_fmpc_config_default(nmpc_b200_fmpc_config * cfg);
+
+  typedef struct nmpc_b200_fmpc nmpc_b200_fmpc;
+
+  int nmpc_b200_fmpc_create(const char * model,
+                            const double * params,
+                            int n_params,
+                            const nmpc_b200_fmpc_config * cfg,
+                            int batch_capacity,
+                            int device,
+                            nmpc_b200_fmpc ** out);
+  int nmpc_b200_fmpc_destroy(nmpc_b200_fmpc * h);
+  int nmpc_b200_fmpc_set_config(nmpc_b200_fmpc * h, const nmpc_b200_fmpc_config * cfg);
+
+  /** FmpcSolver::solve(current_t, current_x, initial_variable) (FmpcSolver.hpp:158-257): x0[B][NX] and
+      the initial Variable as five arrays x[B][N+1][NX], u[B][N][NU], lambda[B][N+1][NX], s[B][N][NG],
+      nu[B][N][NG].  Negative s/nu => NMPC_B200_ERR_RUNTIME (checkVariable, FmpcSolver.hpp:348-361). */
+  int nmpc_b200_fmpc_solve(nmpc_b200_fmpc * h,
+                           int B,
+                           double current_t,
+                           const double * x0,
+                           const double * x,
+                           const double * u,
+                           const double * lambda,
+                           const double * s,
+                           const double * nu,
+                           int n_steps,
+                           int on_device,
+                           void * stream);
+
+  typedef enum
+  {
+    NMPC_B200_FMPC_X = 0, /* variable().x_list       double [B][N+1][NX] */
+    NMPC_B200_FMPC_U = 1, /* variable().u_list       double [B][N][NU] */
+    NMPC_B200_FMPC_LAMBDA = 2, /* variable().lambda_list  double [B][N+1][NX] */
+    NMPC_B200_FMPC_S = 3, /* variable().s_list       double [B][N][NG] */
+    NMPC_B200_FMPC_NU = 4, /* variable().nu_list      double [B][N][NG] */
+    NMPC_B200_FMPC_K_FF = 5, /* coeffList()[i].k        double [B][N][NU] */
+    NMPC_B200_FMPC_K_FB = 6, /* coeffList()[i].K        double [B][N][NU*NX] */
+    NMPC_B200_FMPC_TRACE = 7, /* traceDataList()         double [B][max_iter][5]: iter kkt_error barrier_eps
+                                 alpha_s alpha_nu */
+    NMPC_B200_FMPC_STATUS = 8, /* FmpcSolver::Status      int [B] (FmpcSolver.h:92-114) */
+    NMPC_B200_FMPC_N_TRACE = 9, /* traceDataList().size()  int [B] */
+    NMPC_B200_FMPC_U0 = 10 /* u_list[0]               double [B][NU] */
+  } nmpc_b200_fmpc_field;
+
+  int nmpc_b200_fmpc_get(nmpc_b200_fmpc * h, int what, void * dst, size_t dst_bytes, int dst_on_device, void * stream);
+  int nmpc_b200_fmpc_sync(nmpc_b200_fmpc * h);
+  int nmpc_b200_fmpc_enable_timing(nmpc_b200_fmpc * h, int enable);
+  /** ms[8] = {solve, setup, opt, coeff, backward, forward, update, copy}; launches[4] = {coeff,
+      backward, forward, update}. */
+  int nmpc_b200_fmpc_get_durations(nmpc_b200_fmpc * h, double * ms, int * launches);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NMPC_B200_C_API_H */

@@ -1,0 +1,495 @@
+/* nmpc_b200 -- host side of the batched DDP engine for one functor type M.
+ *
+ * Owns the device workspace for `capacity` instances, converts the instance-major arrays of the
+ * C ABI to the batch-innermost device layout, and enqueues K0, then max_iter x {K1, K2, K3} on one
+ * stream with no host round trip (per-instance lambda/status/iteration counters live on the device;
+ * finished instances' threads return immediately).  For max_iter > kCheckStride the host polls an
+ * active-instance counter every kCheckStride iterations so that a batch that has converged does not
+ * pay for hundreds of empty launches (DDPSolver::Configuration::max_iter defaults to 500).
+ */
+#pragma once
+
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+#include "ddp_kernels.cuh"
+#include "registry.h"
+
+namespace nmpc_b200
+{
+namespace ddp
+{
+constexpr int kCheckStride = 16;
+
+__global__ void count_active_kernel(const int * status, int B, int * counter)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = (b < B) && (status[b] == 0);
+  const unsigned m = __ballot_sync(0xffffffffu, active);
+  if((threadIdx.x & 31) == 0 && m != 0) atomicAdd(counter, __popc(m));
+}
+
+template<class S>
+__global__ void extract_u0_kernel(const S * u0buf, const S * u1buf, const int * sel, double * dst, int B, int NU, int Bp)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= B) return;
+  const S * u = sel[b] ? u1buf : u0buf;
+  for(int d = 0; d < NU; d++) dst[(size_t)b * NU + d] = double(u[(size_t)d * Bp + b]);
+}
+
+template<class M>
+class DdpEngine : public DdpEngineBase
+{
+public:
+  using S = typename M::Scalar;
+  static constexpr int NX = M::NX;
+  static constexpr int NU = M::NU;
+  using L = BlockLayout<NX, NU>;
+
+  DdpEngine(const double * params, const nmpc_b200_ddp_config & cfg, int batch_capacity, int device)
+  : model_(M::fromParams(params)), device_(device), capacity_(batch_capacity)
+  {
+    if(batch_capacity <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "batch_capacity must be positive");
+    DeviceGuard guard(device_);
+    NMPC_CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    NMPC_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&h_counter_), sizeof(int)));
+    Bp_ = ((capacity_ + 127) / 128) * 128;
+    u_lo_.assign(NU, 0.0);
+    u_hi_.assign(NU, 0.0);
+    applyConfig(cfg, true);
+  }
+
+  ~DdpEngine() override
+  {
+    DeviceGuard guard(device_);
+    cudaStreamSynchronize(own_stream_);
+    for(auto e : events_) cudaEventDestroy(e);
+    cudaStreamDestroy(own_stream_);
+    cudaFreeHost(h_counter_);
+  }
+
+  void setConfig(const nmpc_b200_ddp_config & cfg) override
+  {
+    DeviceGuard guard(device_);
+    applyConfig(cfg, false);
+  }
+
+  const nmpc_b200_ddp_config & config() const override
+  {
+    return cfg_;
+  }
+
+  void setInputLimits(const double * lower, const double * upper) override
+  {
+    DeviceGuard guard(device_);
+    std::vector<S> lo(NU), hi(NU);
+    for(int d = 0; d < NU; d++)
+    {
+      u_lo_[d] = lower[d];
+      u_hi_[d] = upper[d];
+      lo[d] = S(lower[d]);
+      hi[d] = S(upper[d]);
+    }
+    NMPC_CUDA_CHECK(cudaMemcpy(d_u_lo_.ptr, lo.data(), sizeof(S) * NU, cudaMemcpyHostToDevice));
+    NMPC_CUDA_CHECK(cudaMemcpy(d_u_hi_.ptr, hi.data(), sizeof(S) * NU, cudaMemcpyHostToDevice));
+    have_limits_ = true;
+  }
+
+  void solve(int B, double current_t, const double * x0, const double * u_init, int n_u_steps, bool on_device, void * stream)
+      override
+  {
+    DeviceGuard guard(device_);
+    const int N = cfg_.horizon_steps;
+    // DDPSolver.hpp:41-45
+    if(n_u_steps != N)
+    {
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "initial_u_list length should be " + std::to_string(N) + " but "
+                                                      + std::to_string(n_u_steps) + ".");
+    }
+    if(B <= 0 || B > capacity_)
+    {
+      throw Error(NMPC_B200_ERR_CAPACITY,
+                  "batch " + std::to_string(B) + " outside (0, capacity " + std::to_string(capacity_) + "]");
+    }
+    if(x0 == nullptr || u_init == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null input array");
+    // DDPSolver.hpp:391-414: the reference throws as soon as the backward pass runs
+    if(cfg_.use_state_eq_second_derivative)
+    {
+      throw Error(NMPC_B200_ERR_RUNTIME, "Vector-tensor product is not implemented yet.");
+    }
+    if(cfg_.with_input_constraint && !have_limits_)
+    {
+      throw Error(NMPC_B200_ERR_RUNTIME, "with_input_constraint is set but no input limits were given");
+    }
+
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : own_stream_;
+    last_stream_ = st;
+    B_ = B;
+    ws_.B = B;
+    prm_.t0 = S(current_t);
+    n_events_used_ = 0;
+    launches_[0] = launches_[1] = launches_[2] = launches_[3] = 0;
+
+    record(st); // 0: start
+    const double * d_x0 = x0;
+    const double * d_u = u_init;
+    if(!on_device)
+    {
+      NMPC_CUDA_CHECK(cudaMemcpyAsync(stage_in_x_.ptr, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
+      NMPC_CUDA_CHECK(
+          cudaMemcpyAsync(stage_in_u_.ptr, u_init, sizeof(double) * (size_t)B * N * NU, cudaMemcpyHostToDevice, st));
+      d_x0 = stage_in_x_.ptr;
+      d_u = stage_in_u_.ptr;
+    }
+    record(st); // 1: inputs on device
+    launchScatterRows<double, S>(d_x0, ws_.x[0], B, NX, Bp_, st);
+    launchScatterRows<double, S>(d_u, ws_.u[0], B, N * NU, Bp_, st);
+
+    const int tpb = threadsPerBlock(B);
+    const int grid = (B + tpb - 1) / tpb;
+    rollout_init_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_);
+    launches_[0]++;
+    record(st); // 2: setup done
+
+    const int tpb1 = 128;
+    const dim3 grid1((B + tpb1 - 1) / tpb1, N + 1);
+    iter_event_base_ = n_events_used_;
+    iters_launched_ = 0;
+    for(int iter = 1; iter <= cfg_.max_iter; iter++)
+    {
+      linearize_kernel<M><<<grid1, tpb1, 0, st>>>(model_, ws_, prm_);
+      record(st);
+      backward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      record(st);
+      forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      record(st);
+      launches_[1]++;
+      launches_[2]++;
+      launches_[3]++;
+      iters_launched_ = iter;
+      if(iter % kCheckStride == 0 && iter < cfg_.max_iter)
+      {
+        NMPC_CUDA_CHECK(cudaMemsetAsync(d_counter_.ptr, 0, sizeof(int), st));
+        count_active_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws_.status, B, d_counter_.ptr);
+        NMPC_CUDA_CHECK(cudaMemcpyAsync(h_counter_, d_counter_.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+        if(*h_counter_ == 0) break;
+      }
+    }
+    record(st); // end of optimisation loop
+    NMPC_CUDA_CHECK(cudaGetLastError());
+  }
+
+  void get(int what, void * dst, size_t dst_bytes, bool dst_on_device, void * stream) override
+  {
+    DeviceGuard guard(device_);
+    if(B_ <= 0) throw Error(NMPC_B200_ERR_RUNTIME, "get() before solve()");
+    if(dst == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null destination");
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : last_stream_;
+    const int N = cfg_.horizon_steps;
+    const int B = B_;
+    size_t need = 0;
+    bool is_int = false;
+    const int * int_src = nullptr;
+    int R = 0;
+    switch(what)
+    {
+      case NMPC_B200_DDP_X:
+        R = (N + 1) * NX;
+        break;
+      case NMPC_B200_DDP_U:
+        R = N * NU;
+        break;
+      case NMPC_B200_DDP_COST_LIST:
+        R = N + 1;
+        break;
+      case NMPC_B200_DDP_K_FF:
+        R = N * NU;
+        break;
+      case NMPC_B200_DDP_K_FB:
+        R = N * NU * NX;
+        break;
+      case NMPC_B200_DDP_TRACE:
+        R = (cfg_.max_iter + 1) * kTraceFields;
+        break;
+      case NMPC_B200_DDP_COST:
+        R = 1;
+        break;
+      case NMPC_B200_DDP_U0:
+        R = NU;
+        break;
+      case NMPC_B200_DDP_STATUS:
+        is_int = true;
+        int_src = ws_.status;
+        break;
+      case NMPC_B200_DDP_ITERS:
+        is_int = true;
+        int_src = ws_.iters;
+        break;
+      case NMPC_B200_DDP_N_FORWARD:
+        is_int = true;
+        int_src = ws_.n_fwd;
+        break;
+      case NMPC_B200_DDP_N_BACKWARD:
+        is_int = true;
+        int_src = ws_.n_bwd;
+        break;
+      case NMPC_B200_DDP_N_TRACE:
+        is_int = true;
+        break;
+      default:
+        throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "unknown DDP field " + std::to_string(what));
+    }
+    need = is_int ? sizeof(int) * (size_t)B : sizeof(double) * (size_t)B * R;
+    if(dst_bytes < need)
+    {
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT,
+                  "destination too small: " + std::to_string(dst_bytes) + " < " + std::to_string(need));
+    }
+
+    record(st);
+    if(is_int)
+    {
+      if(what == NMPC_B200_DDP_N_TRACE)
+      {
+        // traceDataList().size() == last iteration + 1
+        std::vector<int> it(B);
+        NMPC_CUDA_CHECK(cudaMemcpyAsync(it.data(), ws_.iters, need, cudaMemcpyDeviceToHost, st));
+        NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+        for(auto & v : it) v += 1;
+        NMPC_CUDA_CHECK(cudaMemcpy(dst, it.data(), need, dst_on_device ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+      }
+      else
+      {
+        NMPC_CUDA_CHECK(
+            cudaMemcpyAsync(dst, int_src, need, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if(!dst_on_device) NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+      record(st);
+      return;
+    }
+
+    double * d_out = dst_on_device ? static_cast<double *>(dst) : stageOut(need);
+    switch(what)
+    {
+      case NMPC_B200_DDP_X:
+        launchGatherRows<S, double>(ws_.x[0], ws_.x[1], ws_.sel, nullptr, 0, 1, d_out, B, R, Bp_, st);
+        break;
+      case NMPC_B200_DDP_U:
+        launchGatherRows<S, double>(ws_.u[0], ws_.u[1], ws_.sel, nullptr, 0, 1, d_out, B, R, Bp_, st);
+        break;
+      case NMPC_B200_DDP_COST_LIST:
+        launchGatherRows<S, double>(ws_.cost[0], ws_.cost[1], ws_.sel, nullptr, 0, 1, d_out, B, R, Bp_, st);
+        break;
+      case NMPC_B200_DDP_K_FF:
+        launchGatherRows<S, double>(ws_.kff, ws_.kff, nullptr, nullptr, 0, 1, d_out, B, R, Bp_, st);
+        break;
+      case NMPC_B200_DDP_K_FB:
+        launchGatherRows<S, double>(ws_.kfb, ws_.kfb, nullptr, nullptr, 0, 1, d_out, B, R, Bp_, st);
+        break;
+      case NMPC_B200_DDP_TRACE:
+        // rows past the last executed iteration were never written: read them as zero
+        launchGatherRows<S, double>(ws_.trace, ws_.trace, nullptr, ws_.iters, 1, kTraceFields, d_out, B, R, Bp_, st);
+        break;
+      case NMPC_B200_DDP_COST:
+        launchGatherRows<S, double>(ws_.cost_sum, ws_.cost_sum, nullptr, nullptr, 0, 1, d_out, B, R, Bp_, st);
+        break;
+      case NMPC_B200_DDP_U0:
+        extract_u0_kernel<S><<<(B + 127) / 128, 128, 0, st>>>(ws_.u[0], ws_.u[1], ws_.sel, d_out, B, NU, Bp_);
+        break;
+    }
+    NMPC_CUDA_CHECK(cudaGetLastError());
+    if(!dst_on_device)
+    {
+      NMPC_CUDA_CHECK(cudaMemcpyAsync(dst, d_out, need, cudaMemcpyDeviceToHost, st));
+      NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    record(st);
+  }
+
+  void sync() override
+  {
+    DeviceGuard guard(device_);
+    NMPC_CUDA_CHECK(cudaStreamSynchronize(last_stream_ ? last_stream_ : own_stream_));
+  }
+
+  void enableTiming(bool enable) override
+  {
+    timing_ = enable;
+  }
+
+  void getDurations(double * ms, int * launches) override
+  {
+    DeviceGuard guard(device_);
+    for(int i = 0; i < 8; i++) ms[i] = 0.0;
+    if(launches)
+      for(int i = 0; i < 4; i++) launches[i] = launches_[i];
+    if(!timing_ || n_events_used_ < 4) return;
+    NMPC_CUDA_CHECK(cudaStreamSynchronize(last_stream_));
+    auto el = [&](int a, int b) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, events_[a], events_[b]);
+      return double(t);
+    };
+    const int end_opt = iter_event_base_ + 3 * iters_launched_;
+    ms[6] = el(0, 1); // copy_in
+    ms[1] = el(1, 2); // setup: layout + initial rollout
+    double der = 0, bwd = 0, fwd = 0;
+    for(int it = 0; it < iters_launched_; it++)
+    {
+      const int e = iter_event_base_ + 3 * it;
+      der += el(e - 1, e);
+      bwd += el(e, e + 1);
+      fwd += el(e + 1, e + 2);
+    }
+    ms[3] = der;
+    ms[4] = bwd;
+    ms[5] = fwd;
+    ms[2] = el(2, end_opt); // opt (includes any active-count polls)
+    ms[0] = el(0, end_opt); // solve
+    // copy_out: every get() since the last solve() recorded a pair after end_opt
+    double out = 0;
+    for(int e = end_opt + 1; e + 1 < n_events_used_; e += 2) out += el(e, e + 1);
+    ms[7] = out;
+  }
+
+protected:
+  static int threadsPerBlock(int B)
+  {
+    if(const char * env = std::getenv("NMPC_B200_TPB"))
+    {
+      int v = std::atoi(env);
+      if(v >= 32 && v <= 256 && v % 32 == 0) return v;
+    }
+    // spread small batches over all 148 SMs: one warp per CTA until every SM has a few warps
+    if(B <= 148 * 32 * 2) return 32;
+    if(B <= 148 * 64 * 4) return 64;
+    return 128;
+  }
+
+  void record(cudaStream_t st)
+  {
+    if(!timing_) return;
+    if(n_events_used_ >= (int)events_.size())
+    {
+      cudaEvent_t e;
+      NMPC_CUDA_CHECK(cudaEventCreate(&e));
+      events_.push_back(e);
+    }
+    NMPC_CUDA_CHECK(cudaEventRecord(events_[n_events_used_], st));
+    n_events_used_++;
+  }
+
+  double * stageOut(size_t bytes)
+  {
+    if(stage_out_.bytes() < bytes) stage_out_.allocate((bytes + sizeof(double) - 1) / sizeof(double));
+    return stage_out_.ptr;
+  }
+
+  void applyConfig(const nmpc_b200_ddp_config & cfg, bool first)
+  {
+    if(cfg.horizon_steps <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "horizon_steps must be positive");
+    if(cfg.max_iter < 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "max_iter must be non-negative");
+    if(cfg.n_alpha < 0 || cfg.n_alpha > kMaxAlpha)
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "alpha_list longer than " + std::to_string(kMaxAlpha));
+    if(cfg.reg_type != 1 && cfg.reg_type != 2 && cfg.reg_type != 0)
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "reg_type must be 1 or 2");
+    const bool realloc_needed = first || cfg.horizon_steps != cfg_.horizon_steps || cfg.max_iter != cfg_.max_iter;
+    cfg_ = cfg;
+    prm_.N = cfg.horizon_steps;
+    prm_.max_iter = cfg.max_iter;
+    prm_.reg_type = cfg.reg_type;
+    prm_.with_input_constraint = cfg.with_input_constraint;
+    prm_.n_alpha = cfg.n_alpha;
+    prm_.initial_lambda = S(cfg.initial_lambda);
+    prm_.initial_dlambda = S(cfg.initial_dlambda);
+    prm_.lambda_factor = S(cfg.lambda_factor);
+    prm_.lambda_min = S(cfg.lambda_min);
+    prm_.lambda_max = S(cfg.lambda_max);
+    prm_.k_rel_norm_thre = S(cfg.k_rel_norm_thre);
+    prm_.lambda_thre = S(cfg.lambda_thre);
+    prm_.cost_update_ratio_thre = S(cfg.cost_update_ratio_thre);
+    prm_.cost_update_thre = S(cfg.cost_update_thre);
+    for(int i = 0; i < kMaxAlpha; i++) prm_.alpha_list[i] = (i < cfg.n_alpha) ? S(cfg.alpha_list[i]) : S(0);
+    if(realloc_needed) allocate();
+  }
+
+  void allocate()
+  {
+    const size_t N = cfg_.horizon_steps;
+    const size_t Bp = Bp_;
+    NMPC_CUDA_CHECK(cudaStreamSynchronize(own_stream_));
+    for(int s = 0; s < 2; s++)
+    {
+      x_[s].allocate((N + 1) * NX * Bp);
+      u_[s].allocate(N * NU * Bp);
+      cost_[s].allocate((N + 1) * Bp);
+      ws_.x[s] = x_[s].ptr;
+      ws_.u[s] = u_[s].ptr;
+      ws_.cost[s] = cost_[s].ptr;
+    }
+    deriv_.allocate(N * L::SIZE * Bp);
+    vterm_.allocate((size_t)(NX + NX * NX) * Bp);
+    kff_.allocate(N * NU * Bp);
+    kfb_.allocate(N * NU * NX * Bp);
+    trace_.allocate((size_t)(cfg_.max_iter + 1) * kTraceFields * Bp);
+    scal_.allocate(5 * Bp);
+    ints_.allocate(5 * Bp);
+    d_u_lo_.allocate(NU > 0 ? NU : 1);
+    d_u_hi_.allocate(NU > 0 ? NU : 1);
+    d_counter_.allocate(1);
+    stage_in_x_.allocate((size_t)capacity_ * NX);
+    stage_in_u_.allocate((size_t)capacity_ * N * NU);
+    NMPC_CUDA_CHECK(cudaMemset(scal_.ptr, 0, scal_.bytes()));
+    NMPC_CUDA_CHECK(cudaMemset(ints_.ptr, 0, ints_.bytes()));
+    ws_.Bp = Bp_;
+    ws_.B = 0;
+    ws_.deriv = deriv_.ptr;
+    ws_.vterm = vterm_.ptr;
+    ws_.kff = kff_.ptr;
+    ws_.kfb = kfb_.ptr;
+    ws_.trace = trace_.ptr;
+    ws_.lambda = scal_.ptr;
+    ws_.dlambda = scal_.ptr + Bp;
+    ws_.cost_sum = scal_.ptr + 2 * Bp;
+    ws_.dV = scal_.ptr + 3 * Bp;
+    ws_.u_lo = d_u_lo_.ptr;
+    ws_.u_hi = d_u_hi_.ptr;
+    ws_.status = ints_.ptr;
+    ws_.sel = ints_.ptr + Bp;
+    ws_.iters = ints_.ptr + 2 * Bp;
+    ws_.n_fwd = ints_.ptr + 3 * Bp;
+    ws_.n_bwd = ints_.ptr + 4 * Bp;
+    if(have_limits_) setInputLimits(u_lo_.data(), u_hi_.data());
+    B_ = 0;
+  }
+
+  M model_;
+  int device_;
+  int capacity_;
+  int Bp_ = 0;
+  int B_ = 0;
+  nmpc_b200_ddp_config cfg_{};
+  SolverParams<S> prm_{};
+  Workspace<S> ws_{};
+  cudaStream_t own_stream_ = nullptr;
+  cudaStream_t last_stream_ = nullptr;
+  DeviceBuffer<S> x_[2], u_[2], cost_[2], deriv_, vterm_, kff_, kfb_, trace_, scal_, d_u_lo_, d_u_hi_;
+  DeviceBuffer<int> ints_, d_counter_;
+  DeviceBuffer<double> stage_in_x_, stage_in_u_, stage_out_;
+  int * h_counter_ = nullptr;
+  std::vector<double> u_lo_, u_hi_;
+  bool have_limits_ = false;
+  bool timing_ = false;
+  std::vector<cudaEvent_t> events_;
+  int n_events_used_ = 0;
+  int iter_event_base_ = 0;
+  int iters_launched_ = 0;
+  int launches_[4] = {0, 0, 0, 0};
+};
+} // namespace ddp
+} // namespace nmpc_b200

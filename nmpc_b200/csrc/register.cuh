@@ -1,0 +1,34 @@
+/* nmpc_b200 -- registration of problem functors (instantiates the kernels for the functor type). */
+#pragma once
+
+#include "ddp_engine.cuh"
+#include "model_eval.cuh"
+#include "registry.h"
+
+namespace nmpc_b200
+{
+template<class M>
+struct DdpRegistrar
+{
+  explicit DdpRegistrar(const char * name)
+  {
+    ModelEntry & e = registryEntry(name);
+    e.nx = M::NX;
+    e.nu = M::NU;
+    e.ng = ineqDimOf<M>();
+    e.n_params = M::NUM_PARAMS;
+    e.default_params = [](double * p) { M::defaultParams(p); };
+    e.make_ddp = [](const double * params, const nmpc_b200_ddp_config & cfg, int cap, int dev) {
+      return std::unique_ptr<DdpEngineBase>(new ddp::DdpEngine<M>(params, cfg, cap, dev));
+    };
+    e.eval = [](const double * params, int dev, int n, const double * t, const double * x, const double * u,
+                const ModelEvalOutputs & out) { modelEval<M>(params, dev, n, t, x, u, out); };
+  }
+};
+} // namespace nmpc_b200
+
+#define NMPC_B200_CONCAT_(a, b) a##b
+#define NMPC_B200_CONCAT(a, b) NMPC_B200_CONCAT_(a, b)
+/** Make functor type MODEL available to nmpc_b200_ddp_create() under NAME. */
+#define NMPC_B200_REGISTER_DDP_MODEL(NAME, ...) \
+  static ::nmpc_b200::DdpRegistrar<__VA_ARGS__> NMPC_B200_CONCAT(nmpc_b200_ddp_registrar_, __COUNTER__)(NAME)

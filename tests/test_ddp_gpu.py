@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA DDP path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (fp64), SURVEY.md 8(d) / BASELINE.md 5:
+  M-ref   (reference termination): max|du| / (1 + max|u|) <= 1e-9, |dcost|/|cost| <= 1e-12,
+          identical iteration count and status per instance.
+  M-fixed (10 forced iterations): |dcost|/|cost| <= 1e-10, relative du <= 1e-6.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+U_TOL_REF = 1e-9
+COST_TOL_REF = 1e-12
+U_TOL_FIXED = 1e-6
+COST_TOL_FIXED = 1e-10
+
+
+def _rel_u(a, b):
+    return np.max(np.abs(a - b), axis=(1, 2)) / (1.0 + np.max(np.abs(b), axis=(1, 2)))
+
+
+def _solve_both(gpu, B, seed, N=100, **cfg_kw):
+    p = O.default_params("cartpole")
+    x0 = O.cartpole_x0(B, seed)
+    u_init = np.zeros((B, N, 1))
+    ocfg = O.ddp_config(horizon_steps=N, **cfg_kw)
+    ref = O.ddp_solve_batch("cartpole", p, ocfg, x0, u_init)
+    solver = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+    c = solver.config()
+    c.horizon_steps = N
+    for k, v in cfg_kw.items():
+        setattr(c, k, v)
+    ok = solver.solve_batch(0.0, x0, u_init)
+    return ref, solver, ok
+
+
+def test_model_functor_matches_oracle(gpu):
+    """Device functor vs the oracle's independent restatement, incl. the reference's check point
+    (TestDDPCartPole.cpp:620-623) and its central-difference derivative check (:629-648)."""
+    rng = np.random.default_rng(7)
+    n = 64
+    x = rng.uniform(-3, 3, (n, 4))
+    x[0] = [1.0, -2.0, 3.0, -4.0]
+    u = rng.uniform(-20, 20, (n, 1))
+    u[0] = 10.0
+    p = O.default_params("cartpole")
+    d = gpu.model_eval("cartpole", 0.0, x, u, params=p)
+    for i in range(n):
+        o = O.model_eval("cartpole", p, 0.0, x[i], u[i])
+        for key in ("x_next", "Fx", "Fu", "Lx", "Lu", "Lxx", "Luu", "Lxu", "Vx", "Vxx"):
+            np.testing.assert_allclose(d[key][i], o[key], rtol=1e-12, atol=1e-13, err_msg=key)
+        assert abs(d["running_cost"][i] - o["running_cost"]) <= 1e-12 * max(1, abs(o["running_cost"]))
+        assert abs(d["terminal_cost"][i] - o["terminal_cost"]) <= 1e-12 * max(1, abs(o["terminal_cost"]))
+    eps = 1e-6
+    Fx = np.zeros((4, 4))
+    for j in range(4):
+        e = np.zeros(4)
+        e[j] = eps
+        xp = gpu.model_eval("cartpole", 0.0, (x[0] + e)[None], u[:1], params=p)["x_next"][0]
+        xm = gpu.model_eval("cartpole", 0.0, (x[0] - e)[None], u[:1], params=p)["x_next"][0]
+        Fx[:, j] = (xp - xm) / (2 * eps)
+    assert np.linalg.norm(d["Fx"][0] - Fx) < 1e-6
+
+
+def test_single_instance_swingup(gpu):
+    """solve() of one instance: x0=(0,pi,0,0), N=100, max_iter=10 (oracle values pinned in test_oracle_ddp)."""
+    solver = gpu.DDPSolver("cartpole", batch_capacity=1)
+    solver.config().max_iter = 10
+    converged = solver.solve(0.0, [0, np.pi, 0, 0], np.zeros((100, 1)))
+    assert converged is True
+    tl = solver.traceDataList()
+    assert [t.iter for t in tl] == list(range(8))
+    want = [498.415022255, 406.088004263, 404.897899816, 404.865142163, 404.86399135, 404.863948982, 404.863947391,
+            404.863947331]
+    np.testing.assert_allclose([t.cost for t in tl], want, rtol=2e-12)
+    assert all(t.alpha == 1.0 for t in tl[1:])
+    cd = solver.controlData()
+    np.testing.assert_allclose(cd.u_list[0, :4, 0],
+                               [18.786169762863928, 18.484618096972063, 18.184692098150514, 17.886397315575014],
+                               rtol=1e-10)
+    assert abs(cd.cost_list[0].sum() - tl[-1].cost) < 1e-9
+
+
+@pytest.mark.parametrize("B,seed", [(1, 11), (37, 5), (256, 0), (1000, 3)])
+def test_parity_reference_termination(gpu, B, seed):
+    """M-ref: max_iter=10 with the reference's termination rules; ragged batch sizes."""
+    ref, solver, ok = _solve_both(gpu, B, seed, max_iter=10)
+    assert np.array_equal(solver.status(), ref["status"])
+    assert np.array_equal(solver.iterations(), ref["iters"])
+    assert np.array_equal(solver.n_forward(), ref["n_fwd"])
+    assert np.array_equal(solver.n_backward(), ref["n_bwd"])
+    assert np.array_equal(ok, ref["status"] == 1)
+    cd = solver.controlData()
+    assert _rel_u(cd.u_list, ref["u"]).max() <= U_TOL_REF
+    assert _rel_u(cd.x_list, ref["x"]).max() <= 1e-8
+    cost = solver.cost()
+    assert np.max(np.abs(cost - ref["cost"]) / np.abs(ref["cost"])) <= COST_TOL_REF
+    assert np.max(np.abs(cd.cost_list.sum(axis=1) - cost) / np.abs(cost)) <= 1e-13
+    # gains and the full trace table
+    assert _rel_u(solver.k_list(), ref["k"]).max() <= 1e-6
+    tr = solver.trace()
+    assert np.array_equal(solver.n_trace(), ref["n_trace"])
+    np.testing.assert_array_equal(tr[:, :, 0], ref["trace"][:, :, 0])
+    np.testing.assert_allclose(tr[:, :, 1:5], ref["trace"][:, :, 1:5], rtol=1e-11, atol=1e-300)
+    np.testing.assert_array_equal(solver.u0(), cd.u_list[:, 0, :])
+
+
+def test_parity_fixed_iterations(gpu):
+    """M-fixed: k_rel_norm_thre = cost_update_thre = 0 forces exactly 10 iterations (roofline mode)."""
+    ref, solver, _ = _solve_both(gpu, 512, 0, max_iter=10, k_rel_norm_thre=0.0, cost_update_thre=0.0)
+    assert np.all(ref["iters"] == 10)
+    assert np.array_equal(solver.iterations(), ref["iters"])
+    cost = solver.cost()
+    assert np.max(np.abs(cost - ref["cost"]) / np.abs(ref["cost"])) <= COST_TOL_FIXED
+    assert _rel_u(solver.controlData().u_list, ref["u"]).max() <= U_TOL_FIXED
+
+
+def test_parity_longer_horizon_and_reg_type2(gpu):
+    ref, solver, _ = _solve_both(gpu, 64, 9, N=200, max_iter=8, reg_type=2)
+    assert np.array_equal(solver.iterations(), ref["iters"])
+    assert np.array_equal(solver.status(), ref["status"])
+    assert _rel_u(solver.controlData().u_list, ref["u"]).max() <= U_TOL_REF
+    assert np.max(np.abs(solver.cost() - ref["cost"]) / np.abs(ref["cost"])) <= COST_TOL_REF
+
+
+def test_lambda_retry_and_failure_paths(gpu):
+    """A negative input weight makes Quu indefinite: the LLT failure rule (pivot <= 0) must drive the
+    same lambda-increase retries, and lambda_max the same failures, as in the oracle."""
+    p = O.default_params("cartpole")
+    p[8] = -5e-4  # running_u < 0
+    B, N = 128, 60
+    x0 = O.cartpole_x0(B, 21)
+    u_init = np.zeros((B, N, 1))
+    for lam_max in (1e10, 1e-3):
+        ocfg = O.ddp_config(horizon_steps=N, max_iter=6, lambda_max=lam_max)
+        ref = O.ddp_solve_batch("cartpole", p, ocfg, x0, u_init)
+        assert (ref["n_bwd"] > ref["iters"]).any(), "test input does not exercise the retry path"
+        solver = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+        c = solver.config()
+        c.horizon_steps, c.max_iter, c.lambda_max = N, 6, lam_max
+        solver.solve_batch(0.0, x0, u_init)
+        assert np.array_equal(solver.status(), ref["status"])
+        assert np.array_equal(solver.n_backward(), ref["n_bwd"])
+        assert np.array_equal(solver.iterations(), ref["iters"])
+        np.testing.assert_allclose(solver.trace()[:, :, 2], ref["trace"][:, :, 2], rtol=1e-12)
+        if lam_max < 1:
+            assert (ref["status"] == -1).any()
+
+
+def test_argument_errors_mirror_reference(gpu):
+    solver = gpu.DDPSolver("cartpole", batch_capacity=8)
+    solver.config().max_iter = 2
+    # DDPSolver.hpp:41-45 std::invalid_argument("initial_u_list length should be 100 but 99.")
+    with pytest.raises(ValueError) as e:
+        solver.solve(0.0, np.zeros(4), np.zeros((99, 1)))
+    assert "initial_u_list length should be 100 but 99." in str(e.value)
+    # DDPSolver.hpp:391-414: second-order dynamics derivatives throw std::runtime_error
+    solver.config().use_state_eq_second_derivative = True
+    with pytest.raises(gpu.NmpcB200Error) as e:
+        solver.solve(0.0, np.zeros(4), np.zeros((100, 1)))
+    assert e.value.code == 2 and "Vector-tensor product is not implemented yet." in e.value.message
+    solver.config().use_state_eq_second_derivative = False
+    with pytest.raises(gpu.NmpcB200Error) as e:
+        solver.solve_batch(0.0, np.zeros((9, 4)), np.zeros((9, 100, 1)))
+    assert e.value.code == 6
+    # max_iter exhausted without convergence => solve() returns false (DDPSolver.hpp:140)
+    assert solver.solve(0.0, [0, np.pi, 0, 0], np.zeros((100, 1))) is False
+    assert solver.status()[0] == 0 and solver.iterations()[0] == 2
+
+
+def test_device_resident_io_and_warm_start(gpu):
+    """Device pointers in/out (torch CUDA tensors) give the same result as host arrays; a second solve
+    warm-started with the previous u_list converges immediately, like the MPC loops of the reference
+    (TestDDPCartPole.cpp:388-396)."""
+    import torch
+
+    B, N = 200, 100
+    x0 = O.cartpole_x0(B, 2)
+    solver = gpu.DDPSolver("cartpole", batch_capacity=B)
+    solver.config().max_iter = 10
+    solver.solve_batch(0.0, x0, np.zeros((B, N, 1)))
+    u_host = solver.controlData().u_list
+    xd = torch.from_numpy(x0).cuda()
+    ud = torch.zeros((B, N, 1), dtype=torch.float64, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        solver.solve_batch(0.0, xd, ud, stream=st, read_status=False)
+        out = torch.empty((B, N, 1), dtype=torch.float64, device="cuda")
+        solver.get_into(1, out, stream=st)
+    st.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), u_host)
+    it0 = solver.iterations().copy()
+    solver.solve_batch(0.0, x0, u_host)
+    assert solver.iterations().mean() < it0.mean() and solver.iterations().max() <= 3
+
+
+def test_large_max_iter_early_exit_matches(gpu):
+    """Default max_iter=500: the host polls for 'all finished'; results equal the oracle's."""
+    ref, solver, _ = _solve_both(gpu, 96, 4, max_iter=500)
+    assert np.array_equal(solver.iterations(), ref["iters"])
+    assert np.array_equal(solver.status(), ref["status"])
+    assert _rel_u(solver.controlData().u_list, ref["u"]).max() <= U_TOL_REF
+    tr = solver.trace()
+    assert tr.shape == (96, 501, 9)
+    assert np.all(tr[np.arange(96), ref["n_trace"] - 1, 0] == ref["iters"])
