@@ -279,7 +279,7 @@ class DDPSolver:
         if out is None:
             out = np.empty(shape, dtype=np.float64)
         ptr, on_dev, keep = _capi.as_device_or_host(out, shape)
-        if not on_dev and keep is not out:
+        if not on_dev and keep.ctypes.data != out.ctypes.data:
             raise InvalidArgument(_capi.ERR_INVALID_ARGUMENT, "out must be a contiguous float64 array")
         nbytes = int(np.prod(shape)) * 8
         check(lib().nmpc_b200_ddp_get(self._h, int(what), ptr, nbytes, int(on_dev), self._stream_ptr(stream)))
