@@ -60,6 +60,8 @@ public:
     Bp_ = ((capacity_ + 127) / 128) * 128;
     u_lo_.assign(NU, 0.0);
     u_hi_.assign(NU, 0.0);
+    NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)backwardSmemBytes(kMaxThreadsPerBlock)));
     applyConfig(cfg, true);
   }
 
@@ -163,9 +165,9 @@ public:
     {
       linearize_kernel<M><<<grid1, tpb1, 0, st>>>(model_, ws_, prm_);
       record(st);
-      backward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      backward_kernel<M><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
       record(st);
-      forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      launchForward(B, tpb, grid, iter, st);
       record(st);
       launches_[1]++;
       launches_[2]++;
@@ -358,12 +360,59 @@ public:
   }
 
 protected:
+  static constexpr int kMaxThreadsPerBlock = 128;
+
+  /** K2 stages two derivative blocks per thread in shared memory (cp.async ring). */
+  static size_t backwardSmemBytes(int tpb)
+  {
+    return 2 * sizeof(S) * (size_t)(L::SIZE + NU) * tpb;
+  }
+
+  /** K3 variant: lanes per instance that evaluate line-search candidates concurrently.  Small
+      batches cannot fill the 148 SMs with one thread per instance, so they spend lanes on speculation. */
+  static int forwardLanesPerInstance(int B)
+  {
+    if(const char * env = std::getenv("NMPC_B200_FWD_GA"))
+    {
+      int v = std::atoi(env);
+      if(v == 1 || v == 4 || v == 16) return v;
+    }
+    if(B <= 148 * 32) return 16; // <= 16 warps per SM
+    if(B <= 148 * 128) return 4;
+    return 1;
+  }
+
+  template<int GA>
+  void launchForwardSpec(int B, int iter, cudaStream_t st)
+  {
+    constexpr int kWarps = 4;
+    constexpr int ipw = 32 / GA;
+    const int grid = (B + kWarps * ipw - 1) / (kWarps * ipw);
+    const size_t smem = sizeof(S) * (size_t)kWarps * 4 * FwdOperands<NX, NU>::SIZE * ipw;
+    forward_spec_kernel<M, GA><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, iter);
+  }
+
+  void launchForward(int B, int tpb, int grid, int iter, cudaStream_t st)
+  {
+    switch(forwardLanesPerInstance(B))
+    {
+      case 16:
+        launchForwardSpec<16>(B, iter, st);
+        break;
+      case 4:
+        launchForwardSpec<4>(B, iter, st);
+        break;
+      default:
+        forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+    }
+  }
+
   static int threadsPerBlock(int B)
   {
     if(const char * env = std::getenv("NMPC_B200_TPB"))
     {
       int v = std::atoi(env);
-      if(v >= 32 && v <= 256 && v % 32 == 0) return v;
+      if(v >= 32 && v <= kMaxThreadsPerBlock && v % 32 == 0) return v;
     }
     // spread small batches over all 148 SMs: one warp per CTA until every SM has a few warps
     if(B <= 148 * 32 * 2) return 32;

@@ -101,6 +101,41 @@ __device__ __forceinline__ S ldStream(const S * p)
   return __ldg(p);
 }
 
+/** 8-byte asynchronous global->shared copy (LDGSTS); completion is tracked per thread. */
+__device__ __forceinline__ void cpAsync8(void * smem_dst, const void * gmem_src)
+{
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cpAsync4(void * smem_dst, const void * gmem_src)
+{
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit()
+{
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template<int N>
+__device__ __forceinline__ void cpAsyncWait()
+{
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+/** Each thread stages its own column of one step's derivative block: smem[e][tid] <- deriv[step][e][b]. */
+template<class S, int SIZE>
+__device__ __forceinline__ void stageBlock(S * stage, const S * __restrict__ blk, size_t Bp, int tpb)
+{
+#pragma unroll
+  for(int e = 0; e < SIZE; e++)
+  {
+    if constexpr(sizeof(S) == 8)
+      cpAsync8(stage + (size_t)e * tpb, blk + (size_t)e * Bp);
+    else
+      cpAsync4(stage + (size_t)e * tpb, blk + (size_t)e * Bp);
+  }
+}
+
 template<class S>
 __device__ __forceinline__ void writeTrace(const Workspace<S> & ws,
                                            int b,
@@ -302,6 +337,8 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
                                               const SolverParams<typename M::Scalar> & prm,
                                               int b,
                                               const typename M::Scalar * __restrict__ us,
+                                              typename M::Scalar * __restrict__ ring,
+                                              int tpb,
                                               typename M::Scalar lambda,
                                               typename M::Scalar & dV0,
                                               typename M::Scalar & dV1,
@@ -321,16 +358,37 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
 
   dV0 = S(0);
   dV1 = S(0);
-  k_rel_norm = S(0);
+  // max_i |k_i| / (|u_i| + 1) is tracked as a (numerator, denominator) pair and divided once
+  S krn_num = S(0), krn_den = S(1);
+
+  // two-stage shared-memory ring, one column per thread: while step i computes, the block of step
+  // i-1 is already in flight (cp.async), so the dependent Riccati chain never waits on HBM
+  // (the u_i needed by the termination test ride along as NU extra ring entries)
+  constexpr int kStageElems = L::SIZE + NU;
+  S * const ring0 = ring + threadIdx.x;
+  S * const ring1 = ring0 + (size_t)kStageElems * tpb;
+  auto stageStep = [&](S * dst, int step) {
+    stageBlock<S, L::SIZE>(dst, ws.deriv + (size_t)step * L::SIZE * Bp + b, Bp, tpb);
+    stageBlock<S, NU>(dst + (size_t)L::SIZE * tpb, us + (size_t)step * NU * Bp + b, Bp, tpb);
+    cpAsyncCommit();
+  };
+  stageStep(ring0, N - 1);
+  int stage = 0;
 
   for(int i = N - 1; i >= 0; i--)
   {
-    const S * blk = ws.deriv + (size_t)i * L::SIZE * Bp + b;
+    const S * const blk = stage ? ring1 : ring0;
+    if(i > 0)
+      stageStep(stage ? ring0 : ring1, i - 1);
+    else
+      cpAsyncCommit();
+    cpAsyncWait<1>();
+    stage ^= 1;
     S Fx[NX * NX], Fu[NX * NU];
 #pragma unroll
-    for(int d = 0; d < NX * NX; d++) Fx[d] = ldStream(blk + (size_t)(L::FX + d) * Bp);
+    for(int d = 0; d < NX * NX; d++) Fx[d] = blk[(size_t)(L::FX + d) * tpb];
 #pragma unroll
-    for(int d = 0; d < NX * NU; d++) Fu[d] = ldStream(blk + (size_t)(L::FU + d) * Bp);
+    for(int d = 0; d < NX * NU; d++) Fu[d] = blk[(size_t)(L::FU + d) * tpb];
 
     // Qu = Lu + Fu^T Vx ; Qx = Lx + Fx^T Vx                                  (:386-388)
     S Qu[NU], Qx[NX];
@@ -340,7 +398,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
       S s = S(0);
 #pragma unroll
       for(int r = 0; r < NX; r++) s += Fu[r + a * NX] * Vx[r];
-      Qu[a] = ldStream(blk + (size_t)(L::LU + a) * Bp) + s;
+      Qu[a] = blk[(size_t)(L::LU + a) * tpb] + s;
     }
 #pragma unroll
     for(int j = 0; j < NX; j++)
@@ -348,7 +406,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
       S s = S(0);
 #pragma unroll
       for(int r = 0; r < NX; r++) s += Fx[r + j * NX] * Vx[r];
-      Qx[j] = ldStream(blk + (size_t)(L::LX + j) * Bp) + s;
+      Qx[j] = blk[(size_t)(L::LX + j) * tpb] + s;
     }
 
     // Tu = Fu^T Vxx (NU x NX), Tx = Fx^T Vxx (NX x NX): products associate left to right as in Eigen
@@ -385,7 +443,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
         S s = S(0);
 #pragma unroll
         for(int r = 0; r < NX; r++) s += Tu[a + r * NU] * Fx[r + j * NX];
-        Qux[a + j * NU] = ldStream(blk + (size_t)(L::LXU + j + a * NX) * Bp) + s;
+        Qux[a + j * NU] = blk[(size_t)(L::LXU + j + a * NX) * tpb] + s;
       }
 #pragma unroll
       for(int c = 0; c < NX; c++)
@@ -393,7 +451,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
         S s = S(0);
 #pragma unroll
         for(int r = 0; r < NX; r++) s += Tx[c + r * NX] * Fx[r + j * NX];
-        Qxx[c + j * NX] = ldStream(blk + (size_t)(L::LXX + c + j * NX) * Bp) + s;
+        Qxx[c + j * NX] = blk[(size_t)(L::LXX + c + j * NX) * tpb] + s;
       }
     }
 #pragma unroll
@@ -404,7 +462,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
         S s = S(0);
 #pragma unroll
         for(int r = 0; r < NX; r++) s += Tu[a + r * NU] * Fu[r + c * NX];
-        Quu[a + c * NU] = ldStream(blk + (size_t)(L::LUU + a + c * NU) * Bp) + s;
+        Quu[a + c * NU] = blk[(size_t)(L::LUU + a + c * NU) * tpb] + s;
       }
 
     // regularisation (:421-441)
@@ -425,7 +483,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
           S s = S(0);
 #pragma unroll
           for(int r = 0; r < NX; r++) s += Tur[a + r * NU] * Fx[r + j * NX];
-          Qux_reg[a + j * NU] = ldStream(blk + (size_t)(L::LXU + j + a * NX) * Bp) + s;
+          Qux_reg[a + j * NU] = blk[(size_t)(L::LXU + j + a * NX) * tpb] + s;
         }
 #pragma unroll
       for(int c = 0; c < NU; c++)
@@ -435,7 +493,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
           S s = S(0);
 #pragma unroll
           for(int r = 0; r < NX; r++) s += Tur[a + r * NU] * Fu[r + c * NX];
-          Quu_F[a + c * NU] = ldStream(blk + (size_t)(L::LUU + a + c * NU) * Bp) + s;
+          Quu_F[a + c * NU] = blk[(size_t)(L::LUU + a + c * NU) * tpb] + s;
         }
     }
     else
@@ -452,25 +510,45 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
     }
 
     // gains: LLT(Quu_F), k = -Quu_F^-1 Qu, K = -Quu_F^-1 Qux_reg           (:500-510)
-    if(!lltInPlace<S, NU>(Quu_F)) return false;
-    S invd[NU];
-#pragma unroll
-    for(int a = 0; a < NU; a++) invd[a] = S(1) / Quu_F[a + a * NU];
     S k[NU], K[NU * NX];
-#pragma unroll
-    for(int a = 0; a < NU; a++) k[a] = Qu[a];
-    lltSolveInPlace<S, NU>(Quu_F, invd, k);
-#pragma unroll
-    for(int a = 0; a < NU; a++) k[a] = -k[a];
-#pragma unroll
-    for(int j = 0; j < NX; j++)
+    if constexpr(NU == 1)
     {
-      S col[NU];
+      // 1x1: the LLT failure rule is "Quu_F <= 0"; L L^T solve == one reciprocal
+      if(Quu_F[0] <= S(0))
+      {
+        cpAsyncWait<0>();
+        return false;
+      }
+      const S inv = S(1) / Quu_F[0];
+      k[0] = -(Qu[0] * inv);
 #pragma unroll
-      for(int a = 0; a < NU; a++) col[a] = Qux_reg[a + j * NU];
-      lltSolveInPlace<S, NU>(Quu_F, invd, col);
+      for(int j = 0; j < NX; j++) K[j] = -(Qux_reg[j] * inv);
+    }
+    else
+    {
+      if(!lltInPlace<S, NU>(Quu_F))
+      {
+        cpAsyncWait<0>();
+        return false;
+      }
+      S invd[NU];
 #pragma unroll
-      for(int a = 0; a < NU; a++) K[a + j * NU] = -col[a];
+      for(int a = 0; a < NU; a++) invd[a] = S(1) / Quu_F[a + a * NU];
+#pragma unroll
+      for(int a = 0; a < NU; a++) k[a] = Qu[a];
+      lltSolveInPlace<S, NU>(Quu_F, invd, k);
+#pragma unroll
+      for(int a = 0; a < NU; a++) k[a] = -k[a];
+#pragma unroll
+      for(int j = 0; j < NX; j++)
+      {
+        S col[NU];
+#pragma unroll
+        for(int a = 0; a < NU; a++) col[a] = Qux_reg[a + j * NU];
+        lltSolveInPlace<S, NU>(Quu_F, invd, col);
+#pragma unroll
+        for(int a = 0; a < NU; a++) K[a + j * NU] = -col[a];
+      }
     }
 
     // cost-to-go (:522-526)
@@ -549,13 +627,23 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
     {
       ws.kff[((size_t)i * NU + a) * Bp + b] = k[a];
       kn += k[a] * k[a];
-      const S uv = us[((size_t)i * NU + a) * Bp + b];
+      const S uv = blk[(size_t)(L::SIZE + a) * tpb];
       un += uv * uv;
     }
 #pragma unroll
     for(int d = 0; d < NU * NX; d++) ws.kfb[((size_t)i * NU * NX + d) * Bp + b] = K[d];
-    k_rel_norm = fmax(k_rel_norm, sqrt(kn) / (sqrt(un) + S(1)));
+    {
+      // |k| / (|u| + 1) > num / den  <=>  |k| * den > num * (|u| + 1)   (both denominators >= 1)
+      const S a_num = (NU == 1) ? fabs(k[0]) : sqrt(kn);
+      const S a_den = ((NU == 1) ? fabs(blk[(size_t)L::SIZE * tpb]) : sqrt(un)) + S(1);
+      if(a_num * krn_den > krn_num * a_den)
+      {
+        krn_num = a_num;
+        krn_den = a_den;
+      }
+    }
   }
+  k_rel_norm = krn_num / krn_den;
   return true;
 }
 
@@ -572,6 +660,10 @@ __global__ void backward_kernel(const __grid_constant__ M model,
   if(b >= ws.B) return;
   if(ws.status[b] != 0) return;
 
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S * ring = reinterpret_cast<S *>(smem_raw);
+  const int tpb = blockDim.x;
+
   S lambda = ws.lambda[b];
   S dlambda = ws.dlambda[b];
   const S * us = ws.u[ws.sel[b]];
@@ -581,7 +673,7 @@ __global__ void backward_kernel(const __grid_constant__ M model,
   for(;;)
   {
     n_bwd++;
-    if(backwardSweep<M>(ws, prm, b, us, lambda, dV0, dV1, k_rel_norm)) break;
+    if(backwardSweep<M>(ws, prm, b, us, ring, tpb, lambda, dV0, dV1, k_rel_norm)) break;
     // increase lambda (:194-204)
     dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
     lambda = fmax(lambda * dlambda, prm.lambda_min);
@@ -617,9 +709,132 @@ __global__ void backward_kernel(const __grid_constant__ M model,
 }
 
 /* ------------------------------------------------------------------------------------ K3 ---- */
-/** procOnce() Steps 3-4 (DDPSolver.hpp:234-339): backtracking line search over alpha_list with
-    forwardPass(alpha) (:537-560) writing the candidate trajectory into the non-current buffer; on
-    success the buffers swap roles (sel ^= 1) instead of the reference's three copies (:285-287). */
+/** forwardPass(alpha) (DDPSolver.hpp:537-560) for instance b from its current trajectory (buffer
+    `sel`).  STORE: write the candidate trajectory into buffer sel^1; otherwise only the candidate's
+    total cost is computed.  Both variants execute the same arithmetic in the same order, so a cost
+    obtained without stores is reproduced bit for bit by the storing run. */
+template<class M, bool STORE>
+__device__ __forceinline__ typename M::Scalar forwardRollout(const M & model,
+                                                             const Workspace<typename M::Scalar> & ws,
+                                                             const SolverParams<typename M::Scalar> & prm,
+                                                             int b,
+                                                             int sel,
+                                                             typename M::Scalar alpha)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  const S * __restrict__ xc = ws.x[sel];
+  const S * __restrict__ uc = ws.u[sel];
+  S * __restrict__ xn = ws.x[sel ^ 1];
+  S * __restrict__ un = ws.u[sel ^ 1];
+  S * __restrict__ cn = ws.cost[sel ^ 1];
+
+  Matrix<S, NX, 1> x;
+#pragma unroll
+  for(int d = 0; d < NX; d++) x[d] = xc[(size_t)d * Bp + b];
+  if(STORE)
+  {
+#pragma unroll
+    for(int d = 0; d < NX; d++) xn[(size_t)d * Bp + b] = x[d]; // candidate x_list[0] (:540)
+  }
+
+  S csum = S(0);
+  // software prefetch: step i+1's operands are loaded while step i computes
+  S xr[NX], ur[NU], kr[NU], Kr[NU * NX];
+#pragma unroll
+  for(int d = 0; d < NX; d++) xr[d] = x[d];
+#pragma unroll
+  for(int d = 0; d < NU; d++) ur[d] = ldStream(uc + (size_t)d * Bp + b);
+#pragma unroll
+  for(int d = 0; d < NU; d++) kr[d] = ldStream(ws.kff + (size_t)d * Bp + b);
+#pragma unroll
+  for(int d = 0; d < NU * NX; d++) Kr[d] = ldStream(ws.kfb + (size_t)d * Bp + b);
+  for(int i = 0; i < N; i++)
+  {
+    S xr_n[NX], ur_n[NU], kr_n[NU], Kr_n[NU * NX];
+    const int ip = (i + 1 < N) ? i + 1 : i;
+#pragma unroll
+    for(int d = 0; d < NX; d++) xr_n[d] = ldStream(xc + ((size_t)ip * NX + d) * Bp + b);
+#pragma unroll
+    for(int d = 0; d < NU; d++) ur_n[d] = ldStream(uc + ((size_t)ip * NU + d) * Bp + b);
+#pragma unroll
+    for(int d = 0; d < NU; d++) kr_n[d] = ldStream(ws.kff + ((size_t)ip * NU + d) * Bp + b);
+#pragma unroll
+    for(int d = 0; d < NU * NX; d++) Kr_n[d] = ldStream(ws.kfb + ((size_t)ip * NU * NX + d) * Bp + b);
+
+    // u' = u + alpha k + K (x' - x)                                       (:545-546)
+    Matrix<S, NU, 1> u;
+#pragma unroll
+    for(int a = 0; a < NU; a++)
+    {
+      S s = S(0);
+#pragma unroll
+      for(int j = 0; j < NX; j++) s += Kr[a + j * NU] * (x[j] - xr[j]);
+      u[a] = (ur[a] + alpha * kr[a]) + s;
+      if(STORE) un[((size_t)i * NU + a) * Bp + b] = u[a];
+    }
+    const S t = prm.t0 + i * model.dt();
+    const S c = model.runningCost(t, x, u);
+    x = model.stateEq(t, x, u);
+    if(STORE)
+    {
+#pragma unroll
+      for(int d = 0; d < NX; d++) xn[((size_t)(i + 1) * NX + d) * Bp + b] = x[d];
+      cn[(size_t)i * Bp + b] = c;
+    }
+    csum += c;
+
+#pragma unroll
+    for(int d = 0; d < NX; d++) xr[d] = xr_n[d];
+#pragma unroll
+    for(int d = 0; d < NU; d++) ur[d] = ur_n[d];
+#pragma unroll
+    for(int d = 0; d < NU; d++) kr[d] = kr_n[d];
+#pragma unroll
+    for(int d = 0; d < NU * NX; d++) Kr[d] = Kr_n[d];
+  }
+  {
+    const S t = prm.t0 + N * model.dt();
+    const S c = model.terminalCost(t, x);
+    if(STORE) cn[(size_t)N * Bp + b] = c;
+    csum += c;
+  }
+  return csum;
+}
+
+/** Acceptance test of one line-search candidate (DDPSolver.hpp:248-264). */
+template<class S>
+__device__ __forceinline__ bool lineSearchTest(const SolverParams<S> & prm,
+                                               S cost_cur,
+                                               S cost_cand,
+                                               S alpha,
+                                               S dV0,
+                                               S dV1,
+                                               S & actual,
+                                               S & expected,
+                                               S & ratio)
+{
+  actual = cost_cur - cost_cand;
+  expected = S(-1) * alpha * (dV0 + alpha * dV1);
+  ratio = actual / expected;
+  if(expected < S(0)) ratio = (actual >= S(0)) ? S(1) : S(-1);
+  return ratio > prm.cost_update_ratio_thre;
+}
+
+/** procOnce() Steps 3-4 (DDPSolver.hpp:234-339): backtracking line search over alpha_list, then the
+    accept/reject bookkeeping.  On success the two trajectory buffers swap roles (sel ^= 1) instead of
+    the reference's three copies (:285-287).
+
+    forwardPass(alpha) is a pure function of (current trajectory, k, K, alpha), so trying the
+    candidates in parallel and keeping the first success in list order gives the reference's result.
+    Every thread first tries alpha_list[0] for its own instance.  The (few) instances for which that
+    fails are then served by the whole warp: the remaining n_alpha-1 candidates of up to
+    32/(n_alpha-1) failed instances are rolled out concurrently, one candidate per lane, without
+    stores; the winner (if any) is rolled out once more by the owning thread with stores.  A warp
+    therefore spends 1 + ceil(F / 3) (+1) rollouts instead of up to 11 when F of its instances need
+    backtracking. */
 template<class M>
 __global__ void forward_kernel(const __grid_constant__ M model,
                                const __grid_constant__ Workspace<typename M::Scalar> ws,
@@ -627,129 +842,138 @@ __global__ void forward_kernel(const __grid_constant__ M model,
                                int iter)
 {
   using S = typename M::Scalar;
-  constexpr int NX = M::NX, NU = M::NU;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if(b >= ws.B) return;
-  if(ws.status[b] != 0) return;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int bg = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int b = (bg < ws.B) ? bg : (ws.B - 1); // keep every lane of the warp alive for the shuffles
+  const bool active = (bg < ws.B) && (ws.status[b] == 0);
   const size_t Bp = ws.Bp;
-  const int N = prm.N;
 
   const int sel = ws.sel[b];
-  const S * __restrict__ xc = ws.x[sel];
-  const S * __restrict__ uc = ws.u[sel];
-  S * __restrict__ xn = ws.x[sel ^ 1];
-  S * __restrict__ un = ws.u[sel ^ 1];
-  S * __restrict__ cn = ws.cost[sel ^ 1];
-
   const S cost_cur = ws.cost_sum[b];
   const S dV0 = ws.dV[b];
   const S dV1 = ws.dV[Bp + b];
-  S lambda = ws.lambda[b];
-  S dlambda = ws.dlambda[b];
-  const S k_rel_norm = ws.trace[((size_t)iter * kTraceFields + 5) * Bp + b];
 
-  bool forward_pass_success = false;
-  S alpha = S(0), cost_update_actual = S(0), cost_update_expected = S(0), cost_update_ratio = S(0);
-  S cost_new = S(0);
-  int n_fwd = ws.n_fwd[b];
+  bool success = false;
+  S alpha = S(0), actual = S(0), expected = S(0), ratio = S(0), cost_new = S(0);
+  int tried = 0;
+  bool need_store_run = false;
 
-  Matrix<S, NX, 1> x0;
-#pragma unroll
-  for(int d = 0; d < NX; d++) x0[d] = xc[(size_t)d * Bp + b];
-#pragma unroll
-  for(int d = 0; d < NX; d++) xn[(size_t)d * Bp + b] = x0[d]; // candidate x_list[0] (:540)
-
-  for(int ai = 0; ai < prm.n_alpha; ai++)
+  if(active && prm.n_alpha > 0)
   {
-    alpha = prm.alpha_list[ai];
-    n_fwd++;
+    alpha = prm.alpha_list[0];
+    cost_new = forwardRollout<M, true>(model, ws, prm, b, sel, alpha);
+    success = lineSearchTest<S>(prm, cost_cur, cost_new, alpha, dV0, dV1, actual, expected, ratio);
+    tried = 1;
+  }
 
-    // forwardPass(alpha)
-    Matrix<S, NX, 1> x = x0;
-    S csum = S(0);
-    // software prefetch of step i+1's operands while step i computes
-    S xr[NX], ur[NU], kr[NU], Kr[NU * NX];
-#pragma unroll
-    for(int d = 0; d < NX; d++) xr[d] = x0[d];
-#pragma unroll
-    for(int d = 0; d < NU; d++) ur[d] = ldStream(uc + (size_t)d * Bp + b);
-#pragma unroll
-    for(int d = 0; d < NU; d++) kr[d] = ldStream(ws.kff + (size_t)d * Bp + b);
-#pragma unroll
-    for(int d = 0; d < NU * NX; d++) Kr[d] = ldStream(ws.kfb + (size_t)d * Bp + b);
-    for(int i = 0; i < N; i++)
+  const int rem = prm.n_alpha - 1;
+  unsigned pending = __ballot_sync(kFull, active && !success && rem > 0);
+  if(rem > 0 && rem <= 32)
+  {
+    const int groups = 32 / rem; // failed instances served per round
+    const int g = lane / rem; // this lane's group in a round
+    const int ai = 1 + lane % rem; // and its candidate
+    while(pending != 0)
     {
-      S xr_n[NX], ur_n[NU], kr_n[NU], Kr_n[NU * NX];
-      const int ip = (i + 1 < N) ? i + 1 : i;
-#pragma unroll
-      for(int d = 0; d < NX; d++) xr_n[d] = ldStream(xc + ((size_t)ip * NX + d) * Bp + b);
-#pragma unroll
-      for(int d = 0; d < NU; d++) ur_n[d] = ldStream(uc + ((size_t)ip * NU + d) * Bp + b);
-#pragma unroll
-      for(int d = 0; d < NU; d++) kr_n[d] = ldStream(ws.kff + ((size_t)ip * NU + d) * Bp + b);
-#pragma unroll
-      for(int d = 0; d < NU * NX; d++) Kr_n[d] = ldStream(ws.kfb + ((size_t)ip * NU * NX + d) * Bp + b);
-
-      // u' = u + alpha k + K (x' - x)                                       (:545-546)
-      Matrix<S, NU, 1> u;
-#pragma unroll
-      for(int a = 0; a < NU; a++)
+      // owners of this round: the `groups` lowest set bits of `pending`
+      unsigned m = pending;
+      int src = -1;
+      for(int q = 0; q < groups && m != 0; q++)
       {
-        S s = S(0);
-#pragma unroll
-        for(int j = 0; j < NX; j++) s += Kr[a + j * NU] * (x[j] - xr[j]);
-        u[a] = (ur[a] + alpha * kr[a]) + s;
-        un[((size_t)i * NU + a) * Bp + b] = u[a];
+        const int l = __ffs(m) - 1;
+        if(q == g) src = l;
+        m &= m - 1;
       }
-      const S t = prm.t0 + i * model.dt();
-      const S c = model.runningCost(t, x, u);
-      x = model.stateEq(t, x, u);
-#pragma unroll
-      for(int d = 0; d < NX; d++) xn[((size_t)(i + 1) * NX + d) * Bp + b] = x[d];
-      cn[(size_t)i * Bp + b] = c;
-      csum += c;
+      const unsigned round_mask = pending & ~m;
+      pending = m;
+      const bool worker = (g < groups) && (src >= 0);
+      const int s_lane = worker ? src : lane;
+      const int w_b = __shfl_sync(kFull, b, s_lane);
+      const int w_sel = __shfl_sync(kFull, sel, s_lane);
+      const S w_cost = __shfl_sync(kFull, cost_cur, s_lane);
+      const S w_dV0 = __shfl_sync(kFull, dV0, s_lane);
+      const S w_dV1 = __shfl_sync(kFull, dV1, s_lane);
 
-#pragma unroll
-      for(int d = 0; d < NX; d++) xr[d] = xr_n[d];
-#pragma unroll
-      for(int d = 0; d < NU; d++) ur[d] = ur_n[d];
-#pragma unroll
-      for(int d = 0; d < NU; d++) kr[d] = kr_n[d];
-#pragma unroll
-      for(int d = 0; d < NU * NX; d++) Kr[d] = Kr_n[d];
-    }
-    {
-      const S t = prm.t0 + N * model.dt();
-      const S c = model.terminalCost(t, x);
-      cn[(size_t)N * Bp + b] = c;
-      csum += c;
-    }
+      S w_actual = S(0), w_expected = S(0), w_ratio = S(0), w_costn = S(0);
+      bool w_ok = false;
+      if(worker)
+      {
+        const S w_alpha = prm.alpha_list[ai];
+        w_costn = forwardRollout<M, false>(model, ws, prm, w_b, w_sel, w_alpha);
+        w_ok = lineSearchTest<S>(prm, w_cost, w_costn, w_alpha, w_dV0, w_dV1, w_actual, w_expected, w_ratio);
+      }
+      const unsigned ok_ballot = __ballot_sync(kFull, worker && w_ok);
 
-    // (:248-264)
-    cost_new = csum;
-    cost_update_actual = cost_cur - csum;
-    cost_update_expected = S(-1) * alpha * (dV0 + alpha * dV1);
-    cost_update_ratio = cost_update_actual / cost_update_expected;
-    if(cost_update_expected < S(0))
-    {
-      cost_update_ratio = (cost_update_actual >= S(0)) ? S(1) : S(-1);
+      // each owner looks up its group's verdict: first success in list order, else the last candidate
+      const bool owner = active && ((round_mask >> lane) & 1u);
+      int res_lane = lane;
+      int win = -1;
+      if(owner)
+      {
+        const int q = __popc(round_mask & ((1u << lane) - 1u));
+        const unsigned gm = (ok_ballot >> (q * rem)) & ((rem == 32) ? kFull : ((1u << rem) - 1u));
+        win = (gm != 0) ? (__ffs(gm) - 1) : -1;
+        res_lane = q * rem + ((win >= 0) ? win : (rem - 1));
+      }
+      const S r_actual = __shfl_sync(kFull, w_actual, res_lane);
+      const S r_expected = __shfl_sync(kFull, w_expected, res_lane);
+      const S r_ratio = __shfl_sync(kFull, w_ratio, res_lane);
+      const S r_costn = __shfl_sync(kFull, w_costn, res_lane);
+      if(owner)
+      {
+        actual = r_actual;
+        expected = r_expected;
+        ratio = r_ratio;
+        if(win >= 0)
+        {
+          success = true;
+          need_store_run = true;
+          cost_new = r_costn;
+          alpha = prm.alpha_list[1 + win];
+          tried = 2 + win;
+        }
+        else
+        {
+          alpha = prm.alpha_list[rem];
+          tried = 1 + rem;
+        }
+      }
     }
-    if(cost_update_ratio > prm.cost_update_ratio_thre)
+  }
+  else if(active && !success)
+  {
+    // more candidates than lanes: plain serial backtracking
+    for(int a = 1; a < prm.n_alpha; a++)
     {
-      forward_pass_success = true;
-      break;
+      alpha = prm.alpha_list[a];
+      cost_new = forwardRollout<M, true>(model, ws, prm, b, sel, alpha);
+      tried++;
+      success = lineSearchTest<S>(prm, cost_cur, cost_new, alpha, dV0, dV1, actual, expected, ratio);
+      if(success) break;
     }
   }
 
+  if(need_store_run)
+  {
+    // materialise the winning candidate (same arithmetic => same cost as the store-free rollout)
+    cost_new = forwardRollout<M, true>(model, ws, prm, b, sel, alpha);
+  }
+
+  if(!active) return;
+
   // Step 4 (:280-333)
+  S lambda = ws.lambda[b];
+  S dlambda = ws.dlambda[b];
+  const S k_rel_norm = ws.trace[((size_t)iter * kTraceFields + 5) * Bp + b];
   int retval = 0;
   S cost_out = cost_cur;
-  if(forward_pass_success)
+  if(success)
   {
     ws.sel[b] = sel ^ 1;
     ws.cost_sum[b] = cost_new;
     cost_out = cost_new;
-    if(cost_update_actual < prm.cost_update_thre) retval = 1;
+    if(actual < prm.cost_update_thre) retval = 1;
     dlambda = fmin(dlambda / prm.lambda_factor, S(1) / prm.lambda_factor);
     if(lambda >= prm.lambda_min)
       lambda *= dlambda;
@@ -764,11 +988,275 @@ __global__ void forward_kernel(const __grid_constant__ M model,
   }
   ws.lambda[b] = lambda;
   ws.dlambda[b] = dlambda;
-  ws.n_fwd[b] = n_fwd;
+  ws.n_fwd[b] += tried;
   ws.iters[b] = iter;
   if(retval != 0) ws.status[b] = retval;
-  writeTrace<S>(ws, b, iter, S(iter), cost_out, lambda, dlambda, alpha, k_rel_norm, cost_update_actual,
-                cost_update_expected, cost_update_ratio);
+  writeTrace<S>(ws, b, iter, S(iter), cost_out, lambda, dlambda, alpha, k_rel_norm, actual, expected, ratio);
+}
+
+/* --------------------------------------------------------------- K3, small-batch variant ---- */
+/** Operands of one forward step for one instance, staged in shared memory:
+    [ x_i (NX) | u_i (NU) | k_i (NU) | K_i (NU*NX) ] of the CURRENT trajectory. */
+template<int NX, int NU>
+struct FwdOperands
+{
+  static constexpr int X = 0;
+  static constexpr int U = X + NX;
+  static constexpr int KFF = U + NU;
+  static constexpr int KFB = KFF + NU;
+  static constexpr int SIZE = KFB + NU * NX;
+};
+
+/** forwardPass(alpha) with GA lanes per instance sharing one operand ring.  All 32 lanes execute the
+    loop (it contains warp barriers); `work` lanes roll out their own candidate, `do_store` lanes also
+    write the candidate trajectory, `gcopy` groups keep the ring fed.  Same arithmetic as
+    forwardRollout => same costs. */
+template<class M, int GA, int DEPTH>
+__device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model,
+                                                                 const Workspace<typename M::Scalar> & ws,
+                                                                 const SolverParams<typename M::Scalar> & prm,
+                                                                 typename M::Scalar * __restrict__ ring,
+                                                                 int g,
+                                                                 int a,
+                                                                 int b,
+                                                                 int sel,
+                                                                 typename M::Scalar alpha,
+                                                                 bool work,
+                                                                 bool do_store,
+                                                                 bool gcopy)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  using O = FwdOperands<NX, NU>;
+  constexpr int IPW = 32 / GA;
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  const S * __restrict__ xc = ws.x[sel];
+  const S * __restrict__ uc = ws.u[sel];
+  S * __restrict__ xn = ws.x[sel ^ 1];
+  S * __restrict__ un = ws.u[sel ^ 1];
+  S * __restrict__ cn = ws.cost[sel ^ 1];
+
+  // lane a of the group copies operands a, a+GA, ... of step `step` into ring slot `slot`
+  auto issue = [&](int step, int slot) {
+    if(gcopy && step < N)
+    {
+#pragma unroll
+      for(int e0 = 0; e0 < O::SIZE; e0 += GA)
+      {
+        const int e = e0 + a;
+        if(e < O::SIZE)
+        {
+          const S * src;
+          if(e < O::U)
+            src = xc + ((size_t)step * NX + (e - O::X)) * Bp + b;
+          else if(e < O::KFF)
+            src = uc + ((size_t)step * NU + (e - O::U)) * Bp + b;
+          else if(e < O::KFB)
+            src = ws.kff + ((size_t)step * NU + (e - O::KFF)) * Bp + b;
+          else
+            src = ws.kfb + ((size_t)step * NU * NX + (e - O::KFB)) * Bp + b;
+          S * dst = ring + ((size_t)slot * O::SIZE + e) * IPW + g;
+          if constexpr(sizeof(S) == 8)
+            cpAsync8(dst, src);
+          else
+            cpAsync4(dst, src);
+        }
+      }
+    }
+    cpAsyncCommit();
+  };
+
+  Matrix<S, NX, 1> x;
+#pragma unroll
+  for(int d = 0; d < NX; d++) x[d] = xc[(size_t)d * Bp + b];
+  if(do_store)
+  {
+#pragma unroll
+    for(int d = 0; d < NX; d++) xn[(size_t)d * Bp + b] = x[d];
+  }
+
+  __syncwarp(); // previous users of the ring are done
+#pragma unroll
+  for(int s = 0; s < DEPTH; s++) issue(s, s);
+
+  S csum = S(0);
+  int slot = 0;
+  for(int i = 0; i < N; i++)
+  {
+    cpAsyncWait<DEPTH - 1>(); // this lane's copies of step i have landed
+    __syncwarp(); // ... and so have the other lanes'
+    S xr[NX], ur[NU], kr[NU], Kr[NU * NX];
+    const S * op = ring + (size_t)slot * O::SIZE * IPW + g;
+#pragma unroll
+    for(int d = 0; d < NX; d++) xr[d] = op[(size_t)(O::X + d) * IPW];
+#pragma unroll
+    for(int d = 0; d < NU; d++) ur[d] = op[(size_t)(O::U + d) * IPW];
+#pragma unroll
+    for(int d = 0; d < NU; d++) kr[d] = op[(size_t)(O::KFF + d) * IPW];
+#pragma unroll
+    for(int d = 0; d < NU * NX; d++) Kr[d] = op[(size_t)(O::KFB + d) * IPW];
+    __syncwarp(); // everyone has read the slot: refill it with step i + DEPTH
+    issue(i + DEPTH, slot);
+    slot = (slot + 1 == DEPTH) ? 0 : slot + 1;
+
+    if(work)
+    {
+      Matrix<S, NU, 1> u;
+#pragma unroll
+      for(int c = 0; c < NU; c++)
+      {
+        S s = S(0);
+#pragma unroll
+        for(int j = 0; j < NX; j++) s += Kr[c + j * NU] * (x[j] - xr[j]);
+        u[c] = (ur[c] + alpha * kr[c]) + s;
+        if(do_store) un[((size_t)i * NU + c) * Bp + b] = u[c];
+      }
+      const S t = prm.t0 + i * model.dt();
+      const S c = model.runningCost(t, x, u);
+      x = model.stateEq(t, x, u);
+      if(do_store)
+      {
+#pragma unroll
+        for(int d = 0; d < NX; d++) xn[((size_t)(i + 1) * NX + d) * Bp + b] = x[d];
+        cn[(size_t)i * Bp + b] = c;
+      }
+      csum += c;
+    }
+  }
+  cpAsyncWait<0>();
+  if(work)
+  {
+    const S t = prm.t0 + N * model.dt();
+    const S c = model.terminalCost(t, x);
+    if(do_store) cn[(size_t)N * Bp + b] = c;
+    csum += c;
+  }
+  return csum;
+}
+
+/** procOnce() Steps 3-4 for small batches: GA lanes per instance, lane a of a group rolls out
+    candidate alpha_list[round * GA + a]; the first success in list order wins (identical to the
+    reference's sequential backtracking because forwardPass is a pure function of alpha).  Candidate 0
+    stores its trajectory speculatively (it wins in ~90 % of all line searches); any other winner is
+    rolled out once more with stores.  With GA = 16 every candidate of the default 11-entry alpha_list
+    is evaluated in one sweep, and a 4096-instance batch fills 2048 warps instead of 128. */
+template<class M, int GA>
+__global__ void forward_spec_kernel(const __grid_constant__ M model,
+                                    const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                    const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                    int iter)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  constexpr int IPW = 32 / GA;
+  constexpr int DEPTH = 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr unsigned kGroupMask = (GA == 32) ? kFull : ((1u << GA) - 1u);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / GA;
+  const int a = lane % GA;
+  S * ring = reinterpret_cast<S *>(smem_raw) + (size_t)warp * DEPTH * FwdOperands<NX, NU>::SIZE * IPW;
+
+  const int bg = (blockIdx.x * (blockDim.x >> 5) + warp) * IPW + g;
+  const int b = (bg < ws.B) ? bg : (ws.B - 1);
+  const bool active = (bg < ws.B) && (ws.status[b] == 0);
+  const size_t Bp = ws.Bp;
+  const int sel = ws.sel[b];
+  const S cost_cur = ws.cost_sum[b];
+  const S dV0 = ws.dV[b];
+  const S dV1 = ws.dV[Bp + b];
+
+  bool success = false;
+  int win_ai = -1;
+  S alpha = S(0), actual = S(0), expected = S(0), ratio = S(0), cost_new = S(0);
+
+  const int rounds = (prm.n_alpha + GA - 1) / GA;
+  for(int round = 0; round < rounds; round++)
+  {
+    const int ai = round * GA + a;
+    const bool work = active && !success && (ai < prm.n_alpha);
+    const unsigned work_ballot = __ballot_sync(kFull, work);
+    if(work_ballot == 0) break;
+    const bool gcopy = ((work_ballot >> (g * GA)) & kGroupMask) != 0;
+    const S my_alpha = prm.alpha_list[(ai < prm.n_alpha) ? ai : 0];
+    const S my_cost = forwardRolloutRing<M, GA, DEPTH>(model, ws, prm, ring, g, a, b, sel, my_alpha, work,
+                                                       work && (ai == 0), gcopy);
+    S my_actual = S(0), my_expected = S(0), my_ratio = S(0);
+    bool ok = false;
+    if(work) ok = lineSearchTest<S>(prm, cost_cur, my_cost, my_alpha, dV0, dV1, my_actual, my_expected, my_ratio);
+    const unsigned ok_ballot = __ballot_sync(kFull, ok);
+    const unsigned gm = (ok_ballot >> (g * GA)) & kGroupMask;
+    // verdict of this round for the group: first success, else the last candidate tried
+    const int n_here = min(GA, prm.n_alpha - round * GA);
+    const int pick = (gm != 0) ? (__ffs(gm) - 1) : (n_here - 1);
+    const bool take = active && !success;
+    const int src = take ? (g * GA + pick) : lane;
+    const S r_actual = __shfl_sync(kFull, my_actual, src);
+    const S r_expected = __shfl_sync(kFull, my_expected, src);
+    const S r_ratio = __shfl_sync(kFull, my_ratio, src);
+    const S r_cost = __shfl_sync(kFull, my_cost, src);
+    const S r_alpha = __shfl_sync(kFull, my_alpha, src);
+    if(take)
+    {
+      actual = r_actual;
+      expected = r_expected;
+      ratio = r_ratio;
+      alpha = r_alpha;
+      if(gm != 0)
+      {
+        success = true;
+        win_ai = round * GA + pick;
+        cost_new = r_cost;
+      }
+    }
+  }
+
+  // a winner other than candidate 0 has not been stored yet
+  const bool need = active && success && (win_ai != 0);
+  const unsigned need_ballot = __ballot_sync(kFull, need && a == 0);
+  if(need_ballot != 0)
+  {
+    const S c2 = forwardRolloutRing<M, GA, DEPTH>(model, ws, prm, ring, g, a, b, sel, alpha, need && a == 0,
+                                                  need && a == 0, need);
+    if(need && a == 0) cost_new = c2; // bit-identical to the store-free rollout of the same candidate
+  }
+
+  if(!active || a != 0) return;
+
+  // Step 4 (:280-333)
+  const int tried = success ? (win_ai + 1) : prm.n_alpha;
+  S lambda = ws.lambda[b];
+  S dlambda = ws.dlambda[b];
+  const S k_rel_norm = ws.trace[((size_t)iter * kTraceFields + 5) * Bp + b];
+  int retval = 0;
+  S cost_out = cost_cur;
+  if(success)
+  {
+    ws.sel[b] = sel ^ 1;
+    ws.cost_sum[b] = cost_new;
+    cost_out = cost_new;
+    if(actual < prm.cost_update_thre) retval = 1;
+    dlambda = fmin(dlambda / prm.lambda_factor, S(1) / prm.lambda_factor);
+    if(lambda >= prm.lambda_min)
+      lambda *= dlambda;
+    else
+      lambda = S(0);
+  }
+  else
+  {
+    dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
+    lambda = fmax(lambda * dlambda, prm.lambda_min);
+    if(lambda > prm.lambda_max) retval = -1;
+  }
+  ws.lambda[b] = lambda;
+  ws.dlambda[b] = dlambda;
+  ws.n_fwd[b] += tried;
+  ws.iters[b] = iter;
+  if(retval != 0) ws.status[b] = retval;
+  writeTrace<S>(ws, b, iter, S(iter), cost_out, lambda, dlambda, alpha, k_rel_norm, actual, expected, ratio);
 }
 } // namespace ddp
 } // namespace nmpc_b200
