@@ -24,7 +24,7 @@ namespace ddp
 {
 constexpr int kCheckStride = 16;
 
-__global__ void count_active_kernel(const int * status, int B, int * counter)
+static __global__ void count_active_kernel(const int * status, int B, int * counter)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = (b < B) && (status[b] == 0);

@@ -1,0 +1,862 @@
+/* nmpc_b200 -- FMPC (multiple shooting + primal-dual interior point + Riccati recursion) stage kernels.
+ *
+ * Reference: isri-aist/NMPC nmpc_fmpc/include/nmpc_fmpc/FmpcSolver.hpp.  Same mapping as the DDP
+ * kernels: one thread per instance for the sequential sweeps, one thread per (instance, step) for
+ * the embarrassingly parallel stages; batch index innermost in every array.
+ *
+ *   F0 fmpc_init_kernel      solve(): status/trace reset, optional init_complementary_variable  :166-188
+ *   F1 fmpc_coeff_kernel     procOnce() Step 1 + per-step KKT residual terms                    :401-440, :496-521
+ *   F2 fmpc_backward_kernel  barrier update, KKT test, backwardPass() (same Riccati sweep shape
+ *                            as ddp::backward_kernel plus the C/D slack terms)                  :377-399, :443-448, :524-665
+ *   F3 fmpc_forward_kernel   forwardPass() + fraction-to-boundary rule                          :668-708, :714-750
+ *   F4 fmpc_update_kernel    updateVariables() element-wise part                                :802-831
+ *
+ * Device layout (Bp = padded batch):
+ *   var   x[N+1][NX], u[N][NU], lam[N+1][NX], s[N][NG], nu[N][NG]     (each [..][Bp]), updated in place
+ *   delta same shapes
+ *   coeff [N][CSIZE][Bp]  {A, B, C, D, Lxx, Luu, Lxu, x_bar, g_bar, Lx_bar, Lu_bar}
+ *   term  [NX + NX*NX + NX][Bp]   terminal {Lx, Lxx, Lx_bar}
+ *   gains k[N][NU], K[N][NU*NX], sv[N+1][NX], P[N+1][NX*NX]
+ *   kkt   [N+2][Bp]  squared residual terms: [0] initial-state, [1..N] per step, [N+1] terminal
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <nmpc_b200/matrix.h>
+
+namespace nmpc_b200
+{
+namespace fmpc
+{
+constexpr int kTraceFields = 5; // iter, kkt_error, barrier_eps, alpha_s, alpha_nu
+
+// FmpcSolver::Status (FmpcSolver.h:92-114)
+constexpr int kUninitialized = 0;
+constexpr int kSucceeded = 1;
+constexpr int kErrorInForward = 2;
+constexpr int kErrorInBackward = 3;
+constexpr int kErrorInUpdate = 4;
+constexpr int kMaxIterationReached = 5;
+constexpr int kIterationContinued = 6;
+
+template<class S>
+struct SolverParams
+{
+  int N;
+  int max_iter;
+  int check_nan;
+  int init_complementary_variable;
+  int update_barrier_eps;
+  int break_if_llt_fails;
+  S t0;
+  S kkt_error_thre;
+  S initial_barrier_eps;
+};
+
+template<class S>
+struct Workspace
+{
+  int B;
+  int Bp;
+  S * x0; //!< [NX][Bp] current_x
+  S * x;
+  S * u;
+  S * lam;
+  S * s;
+  S * nu;
+  S * dx;
+  S * du;
+  S * dlam;
+  S * ds;
+  S * dnu;
+  S * coeff;
+  S * term;
+  S * kff;
+  S * kfb;
+  S * sv;
+  S * P;
+  S * kkt;
+  S * trace; //!< [max_iter][5][Bp]
+  S * barrier_eps; //!< [Bp]
+  S * alpha; //!< [2][Bp] alpha_s, alpha_nu of the current iteration
+  int * status;
+  int * n_trace;
+  int * bad_input; //!< [1] set when an initial s / nu is negative (checkVariable)
+};
+
+template<int NX, int NU, int NG>
+struct CoeffLayout
+{
+  static constexpr int A = 0;
+  static constexpr int B = A + NX * NX;
+  static constexpr int C = B + NX * NU;
+  static constexpr int D = C + NG * NX;
+  static constexpr int LXX = D + NG * NU;
+  static constexpr int LUU = LXX + NX * NX;
+  static constexpr int LXU = LUU + NU * NU;
+  static constexpr int XBAR = LXU + NX * NU;
+  static constexpr int GBAR = XBAR + NX;
+  static constexpr int LXBAR = GBAR + NG;
+  static constexpr int LUBAR = LXBAR + NX;
+  static constexpr int SIZE = LUBAR + NU;
+  // terminal entry
+  static constexpr int T_LX = 0;
+  static constexpr int T_LXX = NX;
+  static constexpr int T_LXBAR = NX + NX * NX;
+  static constexpr int T_SIZE = NX + NX * NX + NX;
+};
+
+template<class S>
+__device__ __forceinline__ bool finite(S v)
+{
+  return !(isnan(v) || isinf(v));
+}
+
+/* ------------------------------------------------------------------------------------ F0 ---- */
+/** solve() prologue per (instance, step): optional init_complementary_variable (FmpcSolver.hpp:172-188)
+    and the non-negativity part of checkVariable (:348-361); step 0 also resets the per-instance state. */
+template<class M>
+__global__ void fmpc_init_kernel(const __grid_constant__ M model,
+                                 const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                 const __grid_constant__ SolverParams<typename M::Scalar> prm)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if(b >= ws.B) return;
+  const size_t Bp = ws.Bp;
+  if(i == 0)
+  {
+    ws.status[b] = kIterationContinued;
+    ws.n_trace[b] = 0;
+    // init_complementary_variable resets the barrier parameter (:178); otherwise the member keeps its
+    // value from the previous solve() -- the engine seeds it with initial_barrier_eps
+    ws.barrier_eps[b] = prm.initial_barrier_eps;
+  }
+  if(prm.init_complementary_variable)
+  {
+    const S margin_rate = S(1e-2);
+    const S var_min = S(1e-2);
+    const S eps0 = S(1e-4);
+    Matrix<S, NX, 1> x;
+    Matrix<S, NU, 1> u;
+#pragma unroll
+    for(int d = 0; d < NX; d++) x[d] = ws.x[((size_t)i * NX + d) * Bp + b];
+#pragma unroll
+    for(int d = 0; d < NU; d++) u[d] = ws.u[((size_t)i * NU + d) * Bp + b];
+    const S t = prm.t0 + i * model.dt();
+    const Matrix<S, NG, 1> g = model.ineqConst(t, x, u);
+#pragma unroll
+    for(int j = 0; j < NG; j++)
+    {
+      const S sj = (S(1) + margin_rate) * fmax(S(-1) * g[j], var_min);
+      const S nj = (S(1) + margin_rate) * fmax(eps0 * (S(1) / sj), var_min);
+      ws.s[((size_t)i * NG + j) * Bp + b] = sj;
+      ws.nu[((size_t)i * NG + j) * Bp + b] = nj;
+    }
+    if(i == 0) ws.barrier_eps[b] = eps0;
+  }
+  else
+  {
+    bool neg = false;
+#pragma unroll
+    for(int j = 0; j < NG; j++)
+    {
+      neg = neg || (ws.s[((size_t)i * NG + j) * Bp + b] < S(0)) || (ws.nu[((size_t)i * NG + j) * Bp + b] < S(0));
+    }
+    if(neg) atomicExch(ws.bad_input, 1);
+  }
+}
+
+/* ------------------------------------------------------------------------------------ F1 ---- */
+/** procOnce() Step 1 (FmpcSolver.hpp:401-440) for (instance b, step i), i == N is the terminal entry;
+    also the squared KKT residual terms of this step (calcKktError with barrier_eps = 0, :496-521). */
+template<class M>
+__global__ void fmpc_coeff_kernel(const __grid_constant__ M model,
+                                  const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                  const __grid_constant__ SolverParams<typename M::Scalar> prm)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
+  using L = CoeffLayout<NX, NU, NG>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if(b >= ws.B) return;
+  if(ws.status[b] != kIterationContinued) return;
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  const S dt = model.dt();
+  const S t = prm.t0 + i * dt;
+
+  Matrix<S, NX, 1> x, lambda;
+#pragma unroll
+  for(int d = 0; d < NX; d++)
+  {
+    x[d] = ws.x[((size_t)i * NX + d) * Bp + b];
+    lambda[d] = ws.lam[((size_t)i * NX + d) * Bp + b];
+  }
+
+  if(i == N)
+  {
+    Matrix<S, NX, 1> Lx;
+    Matrix<S, NX, NX> Lxx;
+    model.calcTerminalCostDeriv(t, x, Lx, Lxx);
+    S kk = S(0);
+#pragma unroll
+    for(int d = 0; d < NX; d++)
+    {
+      const S lxb = Lx[d] - lambda[d]; // (2.25a)
+      ws.term[(size_t)(L::T_LX + d) * Bp + b] = Lx[d];
+      ws.term[(size_t)(L::T_LXBAR + d) * Bp + b] = lxb;
+      kk += lxb * lxb;
+    }
+#pragma unroll
+    for(int d = 0; d < NX * NX; d++) ws.term[(size_t)(L::T_LXX + d) * Bp + b] = Lxx.d[d];
+    ws.kkt[(size_t)(N + 1) * Bp + b] = kk;
+    return;
+  }
+
+  Matrix<S, NX, 1> next_x, next_lambda;
+  Matrix<S, NU, 1> u;
+  Matrix<S, NG, 1> s, nu;
+#pragma unroll
+  for(int d = 0; d < NX; d++)
+  {
+    next_x[d] = ws.x[((size_t)(i + 1) * NX + d) * Bp + b];
+    next_lambda[d] = ws.lam[((size_t)(i + 1) * NX + d) * Bp + b];
+  }
+#pragma unroll
+  for(int d = 0; d < NU; d++) u[d] = ws.u[((size_t)i * NU + d) * Bp + b];
+#pragma unroll
+  for(int d = 0; d < NG; d++)
+  {
+    s[d] = ws.s[((size_t)i * NG + d) * Bp + b];
+    nu[d] = ws.nu[((size_t)i * NG + d) * Bp + b];
+  }
+
+  Matrix<S, NX, NX> A, Lxx;
+  Matrix<S, NX, NU> Bm, Lxu;
+  Matrix<S, NG, NX> C;
+  Matrix<S, NG, NU> D;
+  Matrix<S, NX, 1> Lx;
+  Matrix<S, NU, 1> Lu;
+  Matrix<S, NU, NU> Luu;
+  model.calcStateEqDeriv(t, x, u, A, Bm);
+  model.calcIneqConstDeriv(t, x, u, C, D);
+  model.calcRunningCostDeriv(t, x, u, Lx, Lu, Lxx, Luu, Lxu);
+
+  const Matrix<S, NX, 1> x_bar = model.stateEq(t, x, u) - next_x; // (2.23c)
+  const Matrix<S, NG, 1> g_bar = model.ineqConst(t, x, u) + s; // (2.23d)
+  // (2.25b) Lx_bar = -lambda + dt Lx + A^T next_lambda + C^T nu
+  Matrix<S, NX, 1> Lx_bar;
+#pragma unroll
+  for(int j = 0; j < NX; j++)
+  {
+    S atl = S(0), ctn = S(0);
+#pragma unroll
+    for(int r = 0; r < NX; r++) atl += A(r, j) * next_lambda[r];
+#pragma unroll
+    for(int r = 0; r < NG; r++) ctn += C(r, j) * nu[r];
+    Lx_bar[j] = ((S(-1) * lambda[j] + dt * Lx[j]) + atl) + ctn;
+  }
+  // (2.25c) Lu_bar = dt Lu + B^T next_lambda + D^T nu
+  Matrix<S, NU, 1> Lu_bar;
+#pragma unroll
+  for(int j = 0; j < NU; j++)
+  {
+    S btl = S(0), dtn = S(0);
+#pragma unroll
+    for(int r = 0; r < NX; r++) btl += Bm(r, j) * next_lambda[r];
+#pragma unroll
+    for(int r = 0; r < NG; r++) dtn += D(r, j) * nu[r];
+    Lu_bar[j] = (dt * Lu[j] + btl) + dtn;
+  }
+
+  S * blk = ws.coeff + (size_t)i * L::SIZE * Bp + b;
+#pragma unroll
+  for(int d = 0; d < NX * NX; d++) blk[(size_t)(L::A + d) * Bp] = A.d[d];
+#pragma unroll
+  for(int d = 0; d < NX * NU; d++) blk[(size_t)(L::B + d) * Bp] = Bm.d[d];
+#pragma unroll
+  for(int d = 0; d < NG * NX; d++) blk[(size_t)(L::C + d) * Bp] = C.d[d];
+#pragma unroll
+  for(int d = 0; d < NG * NU; d++) blk[(size_t)(L::D + d) * Bp] = D.d[d];
+#pragma unroll
+  for(int d = 0; d < NX * NX; d++) blk[(size_t)(L::LXX + d) * Bp] = Lxx.d[d];
+#pragma unroll
+  for(int d = 0; d < NU * NU; d++) blk[(size_t)(L::LUU + d) * Bp] = Luu.d[d];
+#pragma unroll
+  for(int d = 0; d < NX * NU; d++) blk[(size_t)(L::LXU + d) * Bp] = Lxu.d[d];
+#pragma unroll
+  for(int d = 0; d < NX; d++) blk[(size_t)(L::XBAR + d) * Bp] = x_bar.d[d];
+#pragma unroll
+  for(int d = 0; d < NG; d++) blk[(size_t)(L::GBAR + d) * Bp] = g_bar.d[d];
+#pragma unroll
+  for(int d = 0; d < NX; d++) blk[(size_t)(L::LXBAR + d) * Bp] = Lx_bar.d[d];
+#pragma unroll
+  for(int d = 0; d < NU; d++) blk[(size_t)(L::LUBAR + d) * Bp] = Lu_bar.d[d];
+
+  // calcKktError terms of this step, added in the reference's order (:506-511)
+  S kk = S(0);
+  kk += x_bar.squaredNorm();
+  kk += g_bar.squaredNorm();
+  kk += Lx_bar.squaredNorm();
+  kk += Lu_bar.squaredNorm();
+  {
+    S comp = S(0);
+#pragma unroll
+    for(int j = 0; j < NG; j++)
+    {
+      const S v = fmax(s[j] * nu[j] - S(0), S(0));
+      comp += v * v;
+    }
+    kk += comp;
+  }
+  ws.kkt[(size_t)(i + 1) * Bp + b] = kk;
+  if(i == 0)
+  {
+    S e0 = S(0);
+#pragma unroll
+    for(int d = 0; d < NX; d++)
+    {
+      const S e = ws.x0[(size_t)d * Bp + b] - x[d];
+      e0 += e * e;
+    }
+    ws.kkt[b] = e0; // (current_x - x_list[0]).squaredNorm()  (:501)
+  }
+}
+
+/* ------------------------------------------------------------------------------------ F2 ---- */
+/** Barrier update (FmpcSolver.hpp:377-399), KKT test (:443-448) and backwardPass() (:524-665). */
+template<class M>
+__global__ void fmpc_backward_kernel(const __grid_constant__ M model,
+                                     const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                     const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                     int iter)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
+  using L = CoeffLayout<NX, NU, NG>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= ws.B) return;
+  if(ws.status[b] != kIterationContinued) return;
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  const S dt = model.dt();
+
+  // trace entry of this iteration (:373-375)
+  ws.n_trace[b] = iter;
+  S * tr = ws.trace + (size_t)(iter - 1) * kTraceFields * Bp + b;
+  tr[0] = S(iter);
+  tr[2 * Bp] = S(0);
+  tr[3 * Bp] = S(0);
+  tr[4 * Bp] = S(0);
+
+  // barrier parameter (:378-399): eps = clamp(0.5 * mean(s . nu), 1e-8, 1e6)
+  S barrier_eps = ws.barrier_eps[b];
+  if(prm.update_barrier_eps)
+  {
+    S s_nu_ave = S(0);
+    for(int i = 0; i < N; i++)
+    {
+      S dotv = S(0);
+#pragma unroll
+      for(int j = 0; j < NG; j++)
+        dotv += ws.s[((size_t)i * NG + j) * Bp + b] * ws.nu[((size_t)i * NG + j) * Bp + b];
+      s_nu_ave += dotv;
+    }
+    s_nu_ave /= S(N * NG);
+    barrier_eps = fmin(fmax(S(0.5) * s_nu_ave, S(1e-8)), S(1e6));
+    ws.barrier_eps[b] = barrier_eps;
+  }
+  tr[2 * Bp] = barrier_eps;
+
+  // KKT error (:443-448, :496-521)
+  {
+    S kkt = S(0);
+    for(int i = 0; i < N + 2; i++) kkt += ws.kkt[(size_t)i * Bp + b];
+    kkt = sqrt(kkt);
+    tr[1 * Bp] = kkt;
+    if(kkt <= prm.kkt_error_thre)
+    {
+      ws.status[b] = kSucceeded;
+      return;
+    }
+  }
+
+  // backwardPass (:524-665)
+  S sv[NX], P[NX * NX];
+  S nan_probe = S(0); // becomes NaN as soon as any coefficient is NaN or infinite (x * 0)
+#pragma unroll
+  for(int d = 0; d < NX; d++)
+  {
+    sv[d] = S(-1) * ws.term[(size_t)(L::T_LXBAR + d) * Bp + b]; // (2.34)
+    ws.sv[((size_t)N * NX + d) * Bp + b] = sv[d];
+    nan_probe += sv[d] * S(0) + ws.term[(size_t)(L::T_LX + d) * Bp + b] * S(0);
+  }
+#pragma unroll
+  for(int d = 0; d < NX * NX; d++)
+  {
+    P[d] = ws.term[(size_t)(L::T_LXX + d) * Bp + b];
+    ws.P[((size_t)N * NX * NX + d) * Bp + b] = P[d];
+    nan_probe += P[d] * S(0);
+  }
+
+  bool llt_failed = false;
+  for(int i = N - 1; i >= 0; i--)
+  {
+    const S * blk = ws.coeff + (size_t)i * L::SIZE * Bp + b;
+    S A[NX * NX], Bm[NX * NU], C[NG * NX], D[NG * NU];
+#pragma unroll
+    for(int d = 0; d < NX * NX; d++) A[d] = __ldg(blk + (size_t)(L::A + d) * Bp);
+#pragma unroll
+    for(int d = 0; d < NX * NU; d++) Bm[d] = __ldg(blk + (size_t)(L::B + d) * Bp);
+#pragma unroll
+    for(int d = 0; d < NG * NX; d++) C[d] = __ldg(blk + (size_t)(L::C + d) * Bp);
+#pragma unroll
+    for(int d = 0; d < NG * NU; d++) D[d] = __ldg(blk + (size_t)(L::D + d) * Bp);
+    S x_bar[NX], g_bar[NG];
+#pragma unroll
+    for(int d = 0; d < NX; d++) x_bar[d] = __ldg(blk + (size_t)(L::XBAR + d) * Bp);
+#pragma unroll
+    for(int d = 0; d < NG; d++) g_bar[d] = __ldg(blk + (size_t)(L::GBAR + d) * Bp);
+
+    // pre-process (:572-583)
+    S nu_s[NG], tilde_sub[NG];
+#pragma unroll
+    for(int j = 0; j < NG; j++)
+    {
+      const S sj = ws.s[((size_t)i * NG + j) * Bp + b];
+      const S nj = ws.nu[((size_t)i * NG + j) * Bp + b];
+      nu_s[j] = nj / sj;
+      tilde_sub[j] = (nu_s[j] * g_bar[j] - nj) + barrier_eps * (S(1) / sj);
+    }
+    // Qxx~ = dt Lxx + C^T diag(nu/s) C ; Quu~ = dt Luu + D^T diag D ; Qxu~ = dt Lxu + C^T diag D   (2.28c-e)
+    S F[NX * NX], H[NX * NU], G[NU * NU];
+#pragma unroll
+    for(int c = 0; c < NX; c++)
+#pragma unroll
+      for(int r = 0; r < NX; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int j = 0; j < NG; j++) acc += (C[j + r * NG] * nu_s[j]) * C[j + c * NG];
+        F[r + c * NX] = dt * __ldg(blk + (size_t)(L::LXX + r + c * NX) * Bp) + acc;
+      }
+#pragma unroll
+    for(int c = 0; c < NU; c++)
+    {
+#pragma unroll
+      for(int r = 0; r < NU; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int j = 0; j < NG; j++) acc += (D[j + r * NG] * nu_s[j]) * D[j + c * NG];
+        G[r + c * NU] = dt * __ldg(blk + (size_t)(L::LUU + r + c * NU) * Bp) + acc;
+      }
+#pragma unroll
+      for(int r = 0; r < NX; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int j = 0; j < NG; j++) acc += (C[j + r * NG] * nu_s[j]) * D[j + c * NG];
+        H[r + c * NX] = dt * __ldg(blk + (size_t)(L::LXU + r + c * NX) * Bp) + acc;
+      }
+    }
+    // Lx~ = Lx_bar + C^T tilde_sub ; Lu~ = Lu_bar + D^T tilde_sub                         (2.28f-g)
+    S Lx_t[NX], Lu_t[NU];
+#pragma unroll
+    for(int r = 0; r < NX; r++)
+    {
+      S acc = S(0);
+#pragma unroll
+      for(int j = 0; j < NG; j++) acc += C[j + r * NG] * tilde_sub[j];
+      Lx_t[r] = __ldg(blk + (size_t)(L::LXBAR + r) * Bp) + acc;
+    }
+#pragma unroll
+    for(int r = 0; r < NU; r++)
+    {
+      S acc = S(0);
+#pragma unroll
+      for(int j = 0; j < NG; j++) acc += D[j + r * NG] * tilde_sub[j];
+      Lu_t[r] = __ldg(blk + (size_t)(L::LUBAR + r) * Bp) + acc;
+    }
+    // AtP = A^T P ; F += AtP A ; H += AtP B ; BtP = B^T P ; G += BtP B                   (2.35b-d)
+    S AtP[NX * NX], BtP[NU * NX];
+#pragma unroll
+    for(int c = 0; c < NX; c++)
+    {
+#pragma unroll
+      for(int r = 0; r < NX; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int q = 0; q < NX; q++) acc += A[q + r * NX] * P[q + c * NX];
+        AtP[r + c * NX] = acc;
+      }
+#pragma unroll
+      for(int r = 0; r < NU; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int q = 0; q < NX; q++) acc += Bm[q + r * NX] * P[q + c * NX];
+        BtP[r + c * NU] = acc;
+      }
+    }
+#pragma unroll
+    for(int c = 0; c < NX; c++)
+#pragma unroll
+      for(int r = 0; r < NX; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int q = 0; q < NX; q++) acc += AtP[r + q * NX] * A[q + c * NX];
+        F[r + c * NX] += acc;
+      }
+#pragma unroll
+    for(int c = 0; c < NU; c++)
+    {
+#pragma unroll
+      for(int r = 0; r < NX; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int q = 0; q < NX; q++) acc += AtP[r + q * NX] * Bm[q + c * NX];
+        H[r + c * NX] += acc;
+      }
+#pragma unroll
+      for(int r = 0; r < NU; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int q = 0; q < NX; q++) acc += BtP[r + q * NU] * Bm[q + c * NX];
+        G[r + c * NU] += acc;
+      }
+    }
+
+    // gain solve (:592-624): k = -G^-1 (B^T (P x_bar - s) + Lu~), K = -G^-1 H^T   (2.35e)
+    S Pxb_s[NX];
+#pragma unroll
+    for(int r = 0; r < NX; r++)
+    {
+      S acc = S(0);
+#pragma unroll
+      for(int q = 0; q < NX; q++) acc += P[r + q * NX] * x_bar[q];
+      Pxb_s[r] = acc - sv[r];
+    }
+    S k[NU], K[NU * NX];
+    if constexpr(NU == 1)
+    {
+      // Eigen::LDLT of a 1x1 matrix always reports Success; solve() divides by the pivot unless
+      // |pivot| <= DBL_MIN, in which case the pseudo-inverse yields 0
+      const S piv = G[0];
+      const bool usable = fabs(piv) > S(2.2250738585072014e-308);
+      S rhs = S(0);
+#pragma unroll
+      for(int q = 0; q < NX; q++) rhs += Bm[q] * Pxb_s[q];
+      rhs += Lu_t[0];
+      k[0] = usable ? S(-1) * (rhs / piv) : S(-0.0);
+#pragma unroll
+      for(int c = 0; c < NX; c++) K[c] = usable ? S(-1) * (H[c] / piv) : S(-0.0);
+    }
+    else
+    {
+      // general NU: unpivoted LDL^T (the reference's diagonal pivoting only reorders exact arithmetic)
+      S Lm[NU * NU], Dg[NU];
+#pragma unroll
+      for(int c = 0; c < NU; c++)
+      {
+        S dsum = G[c + c * NU];
+#pragma unroll
+        for(int q = 0; q < c; q++) dsum -= Lm[c + q * NU] * Lm[c + q * NU] * Dg[q];
+        Dg[c] = dsum;
+#pragma unroll
+        for(int r = c + 1; r < NU; r++)
+        {
+          S v = G[r + c * NU];
+#pragma unroll
+          for(int q = 0; q < c; q++) v -= Lm[r + q * NU] * Lm[c + q * NU] * Dg[q];
+          Lm[r + c * NU] = v / dsum;
+        }
+      }
+      auto solve = [&](S * rhs) {
+#pragma unroll
+        for(int r = 0; r < NU; r++)
+#pragma unroll
+          for(int q = 0; q < r; q++) rhs[r] -= Lm[r + q * NU] * rhs[q];
+#pragma unroll
+        for(int r = 0; r < NU; r++) rhs[r] /= Dg[r];
+#pragma unroll
+        for(int r = NU - 1; r >= 0; r--)
+#pragma unroll
+          for(int q = r + 1; q < NU; q++) rhs[r] -= Lm[q + r * NU] * rhs[q];
+      };
+#pragma unroll
+      for(int r = 0; r < NU; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int q = 0; q < NX; q++) acc += Bm[q + r * NX] * Pxb_s[q];
+        k[r] = acc + Lu_t[r];
+      }
+      solve(k);
+#pragma unroll
+      for(int r = 0; r < NU; r++) k[r] = S(-1) * k[r];
+#pragma unroll
+      for(int c = 0; c < NX; c++)
+      {
+        S col[NU];
+#pragma unroll
+        for(int r = 0; r < NU; r++) col[r] = H[c + r * NX];
+        solve(col);
+#pragma unroll
+        for(int r = 0; r < NU; r++) K[r + c * NU] = S(-1) * col[r];
+      }
+    }
+
+    // post-process (:633-637): s = A^T (s - P x_bar) - Lx~ - H k ; P = F - K^T G K, symmetrised   (2.35a)
+    S s_new[NX];
+#pragma unroll
+    for(int r = 0; r < NX; r++)
+    {
+      S acc = S(0);
+#pragma unroll
+      for(int q = 0; q < NX; q++) acc += A[q + r * NX] * (S(-1) * Pxb_s[q]);
+      S hk = S(0);
+#pragma unroll
+      for(int c = 0; c < NU; c++) hk += H[r + c * NX] * k[c];
+      s_new[r] = (acc - Lx_t[r]) - hk;
+    }
+    S KtG[NX * NU];
+#pragma unroll
+    for(int c = 0; c < NU; c++)
+#pragma unroll
+      for(int r = 0; r < NX; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int q = 0; q < NU; q++) acc += K[q + r * NU] * G[q + c * NU];
+        KtG[r + c * NX] = acc;
+      }
+    S Pn[NX * NX];
+#pragma unroll
+    for(int c = 0; c < NX; c++)
+#pragma unroll
+      for(int r = 0; r < NX; r++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int q = 0; q < NU; q++) acc += KtG[r + q * NX] * K[q + c * NU];
+        Pn[r + c * NX] = F[r + c * NX] - acc;
+      }
+#pragma unroll
+    for(int c = 0; c < NX; c++)
+#pragma unroll
+      for(int r = 0; r < NX; r++) P[r + c * NX] = S(0.5) * (Pn[r + c * NX] + Pn[c + r * NX]);
+#pragma unroll
+    for(int r = 0; r < NX; r++) sv[r] = s_new[r];
+
+    // save gains (:643-646) and feed the NaN probe with everything containsNaN() inspects (:136-152)
+#pragma unroll
+    for(int d = 0; d < NU; d++)
+    {
+      ws.kff[((size_t)i * NU + d) * Bp + b] = k[d];
+      nan_probe += k[d] * S(0);
+    }
+#pragma unroll
+    for(int d = 0; d < NU * NX; d++)
+    {
+      ws.kfb[((size_t)i * NU * NX + d) * Bp + b] = K[d];
+      nan_probe += K[d] * S(0);
+    }
+#pragma unroll
+    for(int d = 0; d < NX; d++)
+    {
+      ws.sv[((size_t)i * NX + d) * Bp + b] = sv[d];
+      nan_probe += sv[d] * S(0);
+    }
+#pragma unroll
+    for(int d = 0; d < NX * NX; d++)
+    {
+      ws.P[((size_t)i * NX * NX + d) * Bp + b] = P[d];
+      nan_probe += P[d] * S(0) + A[d] * S(0);
+    }
+#pragma unroll
+    for(int d = 0; d < NX * NU; d++) nan_probe += Bm[d] * S(0) + H[d] * S(0);
+#pragma unroll
+    for(int d = 0; d < NG * NX; d++) nan_probe += C[d] * S(0);
+#pragma unroll
+    for(int d = 0; d < NG * NU; d++) nan_probe += D[d] * S(0);
+#pragma unroll
+    for(int d = 0; d < NX; d++) nan_probe += x_bar[d] * S(0) + Lx_t[d] * S(0);
+#pragma unroll
+    for(int d = 0; d < NG; d++) nan_probe += g_bar[d] * S(0);
+#pragma unroll
+    for(int d = 0; d < NU; d++) nan_probe += Lu_t[d] * S(0);
+  }
+
+  if(llt_failed || (prm.check_nan && !finite(nan_probe)))
+  {
+    ws.status[b] = kErrorInBackward;
+  }
+}
+
+/* ------------------------------------------------------------------------------------ F3 ---- */
+/** forwardPass() (FmpcSolver.hpp:668-708) and the fraction-to-boundary rule (:714-750). */
+template<class M>
+__global__ void fmpc_forward_kernel(const __grid_constant__ M model,
+                                    const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                    const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                    int iter)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
+  using L = CoeffLayout<NX, NU, NG>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= ws.B) return;
+  if(ws.status[b] != kIterationContinued) return;
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  const S barrier_eps = ws.barrier_eps[b];
+
+  S dx[NX];
+#pragma unroll
+  for(int d = 0; d < NX; d++) dx[d] = ws.x0[(size_t)d * Bp + b] - ws.x[(size_t)d * Bp + b]; // (:670)
+
+  S nan_probe = S(0);
+  S alpha_s_max = S(1), alpha_nu_max = S(1);
+  const S margin_ratio = S(0.995);
+  for(int i = 0; i <= N; i++)
+  {
+    // dlambda_i = P_i dx_i - s_i                                                    (2.33)
+#pragma unroll
+    for(int r = 0; r < NX; r++)
+    {
+      S acc = S(0);
+#pragma unroll
+      for(int q = 0; q < NX; q++) acc += __ldg(ws.P + ((size_t)i * NX * NX + r + q * NX) * Bp + b) * dx[q];
+      const S dl = acc - __ldg(ws.sv + ((size_t)i * NX + r) * Bp + b);
+      ws.dlam[((size_t)i * NX + r) * Bp + b] = dl;
+      ws.dx[((size_t)i * NX + r) * Bp + b] = dx[r];
+      nan_probe += dl * S(0) + dx[r] * S(0);
+    }
+    if(i == N) break;
+
+    const S * blk = ws.coeff + (size_t)i * L::SIZE * Bp + b;
+    // du_i = K_i dx_i + k_i                                                         (2.36)
+    S du[NU];
+#pragma unroll
+    for(int r = 0; r < NU; r++)
+    {
+      S acc = S(0);
+#pragma unroll
+      for(int q = 0; q < NX; q++) acc += __ldg(ws.kfb + ((size_t)i * NU * NX + r + q * NU) * Bp + b) * dx[q];
+      du[r] = acc + __ldg(ws.kff + ((size_t)i * NU + r) * Bp + b);
+      ws.du[((size_t)i * NU + r) * Bp + b] = du[r];
+      nan_probe += du[r] * S(0);
+    }
+    // ds_i = -(C dx + D du + g_bar) ; dnu_i = -(nu (ds + s) - eps) / s               (2.27a-b)
+#pragma unroll
+    for(int j = 0; j < NG; j++)
+    {
+      S cdx = S(0), ddu = S(0);
+#pragma unroll
+      for(int q = 0; q < NX; q++) cdx += __ldg(blk + (size_t)(L::C + j + q * NG) * Bp) * dx[q];
+#pragma unroll
+      for(int q = 0; q < NU; q++) ddu += __ldg(blk + (size_t)(L::D + j + q * NG) * Bp) * du[q];
+      const S dsj = S(-1) * ((cdx + ddu) + __ldg(blk + (size_t)(L::GBAR + j) * Bp));
+      const S sj = ws.s[((size_t)i * NG + j) * Bp + b];
+      const S nj = ws.nu[((size_t)i * NG + j) * Bp + b];
+      const S dnj = S(-1) * (nj * (dsj + sj) - barrier_eps) / sj;
+      ws.ds[((size_t)i * NG + j) * Bp + b] = dsj;
+      ws.dnu[((size_t)i * NG + j) * Bp + b] = dnj;
+      nan_probe += dsj * S(0) + dnj * S(0);
+      // fraction-to-boundary (:729-736)
+      if(dsj < S(0)) alpha_s_max = fmin(alpha_s_max, S(-1) * margin_ratio * sj / dsj);
+      if(dnj < S(0)) alpha_nu_max = fmin(alpha_nu_max, S(-1) * margin_ratio * nj / dnj);
+    }
+    // dx_{i+1} = A dx_i + B du_i + x_bar                                             (2.26b)
+    S dxn[NX];
+#pragma unroll
+    for(int r = 0; r < NX; r++)
+    {
+      S adx = S(0), bdu = S(0);
+#pragma unroll
+      for(int q = 0; q < NX; q++) adx += __ldg(blk + (size_t)(L::A + r + q * NX) * Bp) * dx[q];
+#pragma unroll
+      for(int q = 0; q < NU; q++) bdu += __ldg(blk + (size_t)(L::B + r + q * NX) * Bp) * du[q];
+      dxn[r] = (adx + bdu) + __ldg(blk + (size_t)(L::XBAR + r) * Bp);
+    }
+#pragma unroll
+    for(int r = 0; r < NX; r++) dx[r] = dxn[r];
+  }
+
+  S * tr = ws.trace + (size_t)(iter - 1) * kTraceFields * Bp + b;
+  if(prm.check_nan && !finite(nan_probe))
+  {
+    ws.status[b] = kErrorInForward; // (:698-705)
+    return;
+  }
+  if(!(alpha_s_max > S(0) && alpha_s_max <= S(1) && alpha_nu_max > S(0) && alpha_nu_max <= S(1)))
+  {
+    ws.status[b] = kErrorInUpdate; // (:739-747)
+    return;
+  }
+  ws.alpha[b] = alpha_s_max;
+  ws.alpha[Bp + b] = alpha_nu_max;
+  tr[3 * Bp] = alpha_s_max;
+  tr[4 * Bp] = alpha_nu_max;
+}
+
+/* ------------------------------------------------------------------------------------ F4 ---- */
+/** updateVariables() (FmpcSolver.hpp:802-831) for (instance b, step i): x, u, s += alpha_s * delta;
+    lambda, nu += alpha_nu * delta.  The reference's clamp against numeric_limits<double>::lowest() is a
+    no-op and is not reproduced. */
+template<class M>
+__global__ void fmpc_update_kernel(const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                   const __grid_constant__ SolverParams<typename M::Scalar> prm)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if(b >= ws.B) return;
+  if(ws.status[b] != kIterationContinued) return;
+  const size_t Bp = ws.Bp;
+  const S alpha_s = ws.alpha[b];
+  const S alpha_nu = ws.alpha[Bp + b];
+#pragma unroll
+  for(int d = 0; d < NX; d++)
+  {
+    const size_t o = ((size_t)i * NX + d) * Bp + b;
+    ws.x[o] += alpha_s * ws.dx[o];
+    ws.lam[o] += alpha_nu * ws.dlam[o];
+  }
+  if(i < prm.N)
+  {
+#pragma unroll
+    for(int d = 0; d < NU; d++)
+    {
+      const size_t o = ((size_t)i * NU + d) * Bp + b;
+      ws.u[o] += alpha_s * ws.du[o];
+    }
+#pragma unroll
+    for(int d = 0; d < NG; d++)
+    {
+      const size_t o = ((size_t)i * NG + d) * Bp + b;
+      ws.s[o] += alpha_s * ws.ds[o];
+      ws.nu[o] += alpha_nu * ws.dnu[o];
+    }
+  }
+}
+
+/** After the last iteration: IterationContinued => MaxIterationReached (FmpcSolver.hpp:241-244). */
+static __global__ void fmpc_finalize_kernel(int * status, int B)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b < B && status[b] == kIterationContinued) status[b] = kMaxIterationReached;
+}
+} // namespace fmpc
+} // namespace nmpc_b200

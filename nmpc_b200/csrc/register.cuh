@@ -2,6 +2,7 @@
 #pragma once
 
 #include "ddp_engine.cuh"
+#include "fmpc_engine.cuh"
 #include "model_eval.cuh"
 #include "registry.h"
 
@@ -25,6 +26,25 @@ struct DdpRegistrar
                 const ModelEvalOutputs & out) { modelEval<M>(params, dev, n, t, x, u, out); };
   }
 };
+
+template<class M>
+struct FmpcRegistrar
+{
+  explicit FmpcRegistrar(const char * name)
+  {
+    ModelEntry & e = registryEntry(name);
+    e.nx = M::NX;
+    e.nu = M::NU;
+    e.ng = M::NG;
+    e.n_params = M::NUM_PARAMS;
+    e.default_params = [](double * p) { M::defaultParams(p); };
+    e.make_fmpc = [](const double * params, const nmpc_b200_fmpc_config & cfg, int cap, int dev) {
+      return std::unique_ptr<FmpcEngineBase>(new fmpc::FmpcEngine<M>(params, cfg, cap, dev));
+    };
+    e.eval = [](const double * params, int dev, int n, const double * t, const double * x, const double * u,
+                const ModelEvalOutputs & out) { modelEval<M>(params, dev, n, t, x, u, out); };
+  }
+};
 } // namespace nmpc_b200
 
 #define NMPC_B200_CONCAT_(a, b) a##b
@@ -32,3 +52,6 @@ struct DdpRegistrar
 /** Make functor type MODEL available to nmpc_b200_ddp_create() under NAME. */
 #define NMPC_B200_REGISTER_DDP_MODEL(NAME, ...) \
   static ::nmpc_b200::DdpRegistrar<__VA_ARGS__> NMPC_B200_CONCAT(nmpc_b200_ddp_registrar_, __COUNTER__)(NAME)
+/** Make functor type MODEL (with ineqConst / calcIneqConstDeriv) available to nmpc_b200_fmpc_create() under NAME. */
+#define NMPC_B200_REGISTER_FMPC_MODEL(NAME, ...) \
+  static ::nmpc_b200::FmpcRegistrar<__VA_ARGS__> NMPC_B200_CONCAT(nmpc_b200_fmpc_registrar_, __COUNTER__)(NAME)
