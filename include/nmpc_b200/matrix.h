@@ -13,8 +13,10 @@
 
 #if defined(__CUDACC__)
 #  define NMPC_HD __host__ __device__ __forceinline__
+#  define NMPC_UNROLL _Pragma("unroll")
 #else
 #  define NMPC_HD inline
+#  define NMPC_UNROLL
 #endif
 
 namespace nmpc_b200
@@ -54,33 +56,33 @@ struct Matrix
   }
   NMPC_HD void setZero()
   {
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < R * C; i++) d[i] = S(0);
   }
   NMPC_HD void setConstant(S v)
   {
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < R * C; i++) d[i] = v;
   }
   NMPC_HD void setIdentity()
   {
-#pragma unroll
+NMPC_UNROLL
     for(int j = 0; j < C; j++)
-#pragma unroll
+NMPC_UNROLL
       for(int i = 0; i < R; i++) d[i + j * R] = (i == j) ? S(1) : S(0);
   }
   /** m = v.asDiagonal() */
   NMPC_HD void setDiagonal(const Matrix<S, R, 1> & v)
   {
-#pragma unroll
+NMPC_UNROLL
     for(int j = 0; j < C; j++)
-#pragma unroll
+NMPC_UNROLL
       for(int i = 0; i < R; i++) d[i + j * R] = (i == j) ? v.d[i] : S(0);
   }
   /** m.diagonal().array() += s */
   NMPC_HD void addToDiagonal(S s)
   {
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < (R < C ? R : C); i++) d[i + i * R] += s;
   }
   NMPC_HD static Matrix Zero()
@@ -91,20 +93,20 @@ struct Matrix
   }
   NMPC_HD Matrix & operator*=(S s)
   {
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < R * C; i++) d[i] *= s;
     return *this;
   }
   NMPC_HD Matrix & operator+=(const Matrix & o)
   {
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < R * C; i++) d[i] += o.d[i];
     return *this;
   }
   NMPC_HD S dot(const Matrix & o) const
   {
     S s = S(0);
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < R * C; i++) s += d[i] * o.d[i];
     return s;
   }
@@ -115,14 +117,14 @@ struct Matrix
   NMPC_HD Matrix cwiseProduct(const Matrix & o) const
   {
     Matrix m;
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < R * C; i++) m.d[i] = d[i] * o.d[i];
     return m;
   }
   NMPC_HD Matrix cwiseAbs2() const
   {
     Matrix m;
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < R * C; i++) m.d[i] = d[i] * d[i];
     return m;
   }
@@ -132,7 +134,7 @@ template<class S, int R, int C>
 NMPC_HD Matrix<S, R, C> operator+(const Matrix<S, R, C> & a, const Matrix<S, R, C> & b)
 {
   Matrix<S, R, C> m;
-#pragma unroll
+NMPC_UNROLL
   for(int i = 0; i < R * C; i++) m.d[i] = a.d[i] + b.d[i];
   return m;
 }
@@ -141,7 +143,7 @@ template<class S, int R, int C>
 NMPC_HD Matrix<S, R, C> operator-(const Matrix<S, R, C> & a, const Matrix<S, R, C> & b)
 {
   Matrix<S, R, C> m;
-#pragma unroll
+NMPC_UNROLL
   for(int i = 0; i < R * C; i++) m.d[i] = a.d[i] - b.d[i];
   return m;
 }
@@ -150,7 +152,7 @@ template<class S, int R, int C>
 NMPC_HD Matrix<S, R, C> operator*(S s, const Matrix<S, R, C> & a)
 {
   Matrix<S, R, C> m;
-#pragma unroll
+NMPC_UNROLL
   for(int i = 0; i < R * C; i++) m.d[i] = s * a.d[i];
   return m;
 }
@@ -159,13 +161,13 @@ template<class S, int R, int K, int C>
 NMPC_HD Matrix<S, R, C> operator*(const Matrix<S, R, K> & a, const Matrix<S, K, C> & b)
 {
   Matrix<S, R, C> m;
-#pragma unroll
+NMPC_UNROLL
   for(int j = 0; j < C; j++)
-#pragma unroll
+NMPC_UNROLL
     for(int i = 0; i < R; i++)
     {
       S s = S(0);
-#pragma unroll
+NMPC_UNROLL
       for(int k = 0; k < K; k++) s += a(i, k) * b(k, j);
       m(i, j) = s;
     }

@@ -127,6 +127,11 @@ public:
     {
       throw Error(NMPC_B200_ERR_RUNTIME, "with_input_constraint is set but no input limits were given");
     }
+    if(cfg_.with_input_constraint && !kHasBoxQP)
+    {
+      throw Error(NMPC_B200_ERR_UNSUPPORTED,
+                  "with_input_constraint (BoxQP branch, DDPSolver.hpp:450-497) is not implemented on the device yet");
+    }
 
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : own_stream_;
     last_stream_ = st;
@@ -361,6 +366,7 @@ public:
 
 protected:
   static constexpr int kMaxThreadsPerBlock = 128;
+  static constexpr bool kHasBoxQP = false;
 
   /** K2 stages two derivative blocks per thread in shared memory (cp.async ring). */
   static size_t backwardSmemBytes(int tpb)
