@@ -60,7 +60,9 @@ public:
     Bp_ = ((capacity_ + 127) / 128) * 128;
     u_lo_.assign(NU, 0.0);
     u_hi_.assign(NU, 0.0);
-    NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)backwardSmemBytes(kMaxThreadsPerBlock)));
+    NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)backwardSmemBytes(kMaxThreadsPerBlock)));
     applyConfig(cfg, true);
   }
@@ -170,7 +172,10 @@ public:
     {
       linearize_kernel<M><<<grid1, tpb1, 0, st>>>(model_, ws_, prm_);
       record(st);
-      backward_kernel<M><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
+      if(cfg_.with_input_constraint)
+        backward_kernel<M, true><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
+      else
+        backward_kernel<M, false><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
       record(st);
       launchForward(B, tpb, grid, iter, st);
       record(st);
@@ -366,7 +371,7 @@ public:
 
 protected:
   static constexpr int kMaxThreadsPerBlock = 128;
-  static constexpr bool kHasBoxQP = false;
+  static constexpr bool kHasBoxQP = true;
 
   /** K2 stages two derivative blocks per thread in shared memory (cp.async ring). */
   static size_t backwardSmemBytes(int tpb)

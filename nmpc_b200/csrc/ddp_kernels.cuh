@@ -27,6 +27,8 @@
 
 #include <nmpc_b200/matrix.h>
 
+#include "boxqp.cuh"
+
 namespace nmpc_b200
 {
 namespace ddp
@@ -332,7 +334,7 @@ __device__ __forceinline__ void lltSolveInPlace(const S * l, const S * invd, S *
 
 /** One backwardPass() sweep (DDPSolver.hpp:343-534) with regularisation `lambda`.  Returns false as
     soon as the Cholesky factorisation of Quu_F fails at some step (LLT NumericalIssue, :500-508). */
-template<class M>
+template<class M, bool CONSTRAINED>
 __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar> & ws,
                                               const SolverParams<typename M::Scalar> & prm,
                                               int b,
@@ -374,6 +376,9 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
   };
   stageStep(ring0, N - 1);
   int stage = 0;
+  S k_prev[NU]; // k_list_[i + 1], the BoxQP warm start (:452-467)
+#pragma unroll
+  for(int a = 0; a < NU; a++) k_prev[a] = S(0);
 
   for(int i = N - 1; i >= 0; i--)
   {
@@ -511,7 +516,51 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
 
     // gains: LLT(Quu_F), k = -Quu_F^-1 Qu, K = -Quu_F^-1 Qux_reg           (:500-510)
     S k[NU], K[NU * NX];
-    if constexpr(NU == 1)
+    if constexpr(CONSTRAINED)
+    {
+      // control-limited gains (:450-497): k = argmin 1/2 k^T Quu_F k + Qu^T k, lo - u <= k <= up - u,
+      // warm-started from the next step's k; K rows of clamped inputs are zero
+      S lo[NU], hi[NU], init[NU];
+#pragma unroll
+      for(int a = 0; a < NU; a++)
+      {
+        const S uv = blk[(size_t)(L::SIZE + a) * tpb];
+        lo[a] = ws.u_lo[a] - uv;
+        hi[a] = ws.u_hi[a] - uv;
+        init[a] = (i == N - 1) ? S(0) : k_prev[a];
+      }
+      BoxQPResult<S, NU> qp;
+      boxQpSolve<S, NU>(Quu_F, Qu, lo, hi, init, qp);
+      if(qp.retval < 0)
+      {
+        cpAsyncWait<0>();
+        return false;
+      }
+#pragma unroll
+      for(int a = 0; a < NU; a++) k[a] = qp.x[a];
+#pragma unroll
+      for(int d = 0; d < NU * NX; d++) K[d] = S(0);
+      const int nf = qp.n_free;
+      for(int j = 0; j < NX; j++)
+      {
+        S rhs[NU];
+        for(int r = 0; r < nf; r++) rhs[r] = Qux_reg[qp.free_idxs[r] + j * NU];
+        for(int r = 0; r < nf; r++)
+        {
+          S s = rhs[r];
+          for(int q = 0; q < r; q++) s -= qp.llt_free[r + q * nf] * rhs[q];
+          rhs[r] = s / qp.llt_free[r + r * nf];
+        }
+        for(int r = nf - 1; r >= 0; r--)
+        {
+          S s = rhs[r];
+          for(int q = r + 1; q < nf; q++) s -= qp.llt_free[q + r * nf] * rhs[q];
+          rhs[r] = s / qp.llt_free[r + r * nf];
+        }
+        for(int r = 0; r < nf; r++) K[qp.free_idxs[r] + j * NU] = S(-1) * rhs[r];
+      }
+    }
+    else if constexpr(NU == 1)
     {
       // 1x1: the LLT failure rule is "Quu_F <= 0"; L L^T solve == one reciprocal
       if(Quu_F[0] <= S(0))
@@ -620,6 +669,9 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
 #pragma unroll
       for(int r = 0; r < NX; r++) Vxx[r + j * NX] = S(0.5) * (Vn[r + j * NX] + Vn[j + r * NX]);
 
+#pragma unroll
+    for(int a = 0; a < NU; a++) k_prev[a] = k[a];
+
     // save gains (:529-530) and accumulate max_i |k_i| / (|u_i| + 1) (:217-221)
     S kn = S(0), un = S(0);
 #pragma unroll
@@ -649,7 +701,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
 
 /** procOnce() Step 2 (DDPSolver.hpp:188-231): retry the backward sweep with larger lambda until the
     factorisation succeeds, then the small-gradient termination test. */
-template<class M>
+template<class M, bool CONSTRAINED>
 __global__ void backward_kernel(const __grid_constant__ M model,
                                 const __grid_constant__ Workspace<typename M::Scalar> ws,
                                 const __grid_constant__ SolverParams<typename M::Scalar> prm,
@@ -673,7 +725,7 @@ __global__ void backward_kernel(const __grid_constant__ M model,
   for(;;)
   {
     n_bwd++;
-    if(backwardSweep<M>(ws, prm, b, us, ring, tpb, lambda, dV0, dV1, k_rel_norm)) break;
+    if(backwardSweep<M, CONSTRAINED>(ws, prm, b, us, ring, tpb, lambda, dV0, dV1, k_rel_norm)) break;
     // increase lambda (:194-204)
     dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
     lambda = fmax(lambda * dlambda, prm.lambda_min);

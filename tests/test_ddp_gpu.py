@@ -206,3 +206,53 @@ def test_large_max_iter_early_exit_matches(gpu):
     tr = solver.trace()
     assert tr.shape == (96, 501, 9)
     assert np.all(tr[np.arange(96), ref["n_trace"] - 1, 0] == ref["iters"])
+
+
+@pytest.mark.parametrize("N", [200, 400])
+def test_constrained_config1_first_tick(gpu, N):
+    """BASELINE.json configs[0]: TestDDPCartPole (with_input_constraint, +-15 N, max_iter 3, x0=(0,pi,0,0));
+    N=200 is what the reference's rostest runs (TestDDPCartPole.test:14), N=400 the config's literal text.
+    BoxQP-constrained backward pass on the device vs the oracle (whose BoxQP passes the reference's KATs)."""
+    p = O.default_params("cartpole")
+    lo, hi = np.array([-15.0]), np.array([15.0])
+    x0 = np.array([[0, np.pi, 0, 0]])
+    ref = O.ddp_solve_batch("cartpole", p, O.ddp_config(max_iter=3, horizon_steps=N, with_input_constraint=1), x0,
+                            np.zeros((1, N, 1)), u_lo=lo, u_hi=hi)
+    solver = gpu.DDPSolver("cartpole", params=p, batch_capacity=1)
+    c = solver.config()
+    c.horizon_steps, c.max_iter, c.with_input_constraint = N, 3, True
+    with pytest.raises(gpu.NmpcB200Error):  # limits not set yet
+        solver.solve(0.0, x0[0], np.zeros((N, 1)))
+    solver.setInputLimitsFunc(lambda t: (lo, hi))
+    solver.solve(0.0, x0[0], np.zeros((N, 1)))
+    np.testing.assert_allclose(solver.trace()[0, :, 1], ref["trace"][0, :, 1], rtol=1e-12)
+    assert _rel_u(solver.controlData().u_list, ref["u"]).max() <= U_TOL_REF
+    assert _rel_u(solver.k_list(), ref["k"]).max() <= 1e-7
+    assert _rel_u(solver.K_list().reshape(1, N, -1), ref["K"]).max() <= 1e-7
+    if N == 200:
+        np.testing.assert_allclose(solver.trace()[0, :, 1],
+                                   [991.8952423095, 882.7146741324, 850.4060100400, 843.1435488411], rtol=1e-11)
+
+
+def test_constrained_batch_parity(gpu):
+    """Control-limited DDP on a random batch, tighter limits so that many steps clamp."""
+    B, N = 256, 100
+    p = O.default_params("cartpole")
+    lo, hi = np.array([-6.0]), np.array([9.0])
+    x0 = O.cartpole_x0(B, 12)
+    u_init = np.zeros((B, N, 1))
+    ref = O.ddp_solve_batch("cartpole", p, O.ddp_config(max_iter=12, horizon_steps=N, with_input_constraint=1), x0,
+                            u_init, u_lo=lo, u_hi=hi)
+    solver = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+    c = solver.config()
+    c.max_iter, c.with_input_constraint = 12, True
+    solver.setInputLimitsFunc((lo, hi))
+    solver.solve_batch(0.0, x0, u_init)
+    assert np.array_equal(solver.iterations(), ref["iters"])
+    assert np.array_equal(solver.status(), ref["status"])
+    assert np.array_equal(solver.n_forward(), ref["n_fwd"])
+    K = solver.K_list().reshape(B, N, -1)
+    assert (K == 0).any() and (ref["K"] == 0).any(), "test input does not clamp"
+    assert np.array_equal(K == 0, ref["K"] == 0), "clamped sets differ"
+    assert _rel_u(solver.controlData().u_list, ref["u"]).max() <= U_TOL_REF
+    assert np.max(np.abs(solver.cost() - ref["cost"]) / np.abs(ref["cost"])) <= COST_TOL_REF
