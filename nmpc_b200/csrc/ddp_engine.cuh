@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "ddp_kernels.cuh"
+#include "ddp_backward_coop.cuh"
 #include "registry.h"
 
 namespace nmpc_b200
@@ -172,10 +173,7 @@ public:
     {
       linearize_kernel<M><<<grid1, tpb1, 0, st>>>(model_, ws_, prm_);
       record(st);
-      if(cfg_.with_input_constraint)
-        backward_kernel<M, true><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
-      else
-        backward_kernel<M, false><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
+      launchBackward(B, tpb, grid, iter, st);
       record(st);
       launchForward(B, tpb, grid, iter, st);
       record(st);
@@ -372,6 +370,8 @@ public:
 protected:
   static constexpr int kMaxThreadsPerBlock = 128;
   static constexpr bool kHasBoxQP = true;
+  // group size of the cooperative K2: the power of two >= NX, capped at a warp
+  static constexpr int kCoopGS = (NX <= 1) ? 1 : (NX <= 2) ? 2 : (NX <= 4) ? 4 : (NX <= 8) ? 8 : (NX <= 16) ? 16 : 32;
 
   /** K2 stages two derivative blocks per thread in shared memory (cp.async ring). */
   static size_t backwardSmemBytes(int tpb)
@@ -391,6 +391,51 @@ protected:
     if(B <= 148 * 32) return 16; // <= 16 warps per SM
     if(B <= 148 * 128) return 4;
     return 1;
+  }
+
+  /** K2 variant: lanes per instance (columns of the n_x x n_x matrices are spread over the group). */
+  static int backwardLanesPerInstance(int B)
+  {
+    if(const char * env = std::getenv("NMPC_B200_BWD_GS"))
+    {
+      int v = std::atoi(env);
+      if(v == 1 || v == kCoopGS) return v;
+    }
+    // cooperative groups pay off while one thread per instance cannot fill the warp schedulers
+    return (B <= 148 * 128) ? kCoopGS : 1;
+  }
+
+  template<bool CONSTRAINED>
+  void launchBackwardCoop(int B, int iter, cudaStream_t st)
+  {
+    using C = CoopLayout<M, kCoopGS>;
+    constexpr int kWarps = 2;
+    const int grid = (B + kWarps * C::IPW - 1) / (kWarps * C::IPW);
+    const size_t smem = sizeof(S) * (size_t)kWarps * C::WARP_ELEMS;
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      cudaFuncSetAttribute(backward_coop_kernel<M, kCoopGS, CONSTRAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
+      attr_set = true;
+    }
+    backward_coop_kernel<M, kCoopGS, CONSTRAINED><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, iter);
+  }
+
+  void launchBackward(int B, int tpb, int grid, int iter, cudaStream_t st)
+  {
+    if(backwardLanesPerInstance(B) > 1)
+    {
+      if(cfg_.with_input_constraint)
+        launchBackwardCoop<true>(B, iter, st);
+      else
+        launchBackwardCoop<false>(B, iter, st);
+      return;
+    }
+    if(cfg_.with_input_constraint)
+      backward_kernel<M, true><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
+    else
+      backward_kernel<M, false><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
   }
 
   template<int GA>
