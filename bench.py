@@ -100,6 +100,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the
+    CPU baseline: the thread count is passed to the oracle explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def make_config(O, mode):
     kw = dict(max_iter=MAX_ITER, horizon_steps=N_STEPS)
     if mode == "fixed":
@@ -114,11 +123,11 @@ def cpu_baseline(O, B, seed, mode, min_seconds, native=True):
     cfg = O.ddp_config(**make_config(O, mode))
     x0 = O.cartpole_x0(B, seed)
     u_init = np.zeros((B, N_STEPS, NU))
-    threads = O.lib(native).oracle_num_threads()
-    O.ddp_solve_batch("cartpole", p, cfg, x0[:64], u_init[:64], native=native, outputs=False)  # warm-up
+    threads = host_threads()
+    O.ddp_solve_batch("cartpole", p, cfg, x0[:64], u_init[:64], native=native, outputs=False, nthreads=threads)
     done, t0 = 0, time.perf_counter()
     while True:
-        O.ddp_solve_batch("cartpole", p, cfg, x0, u_init, native=native, outputs=False)
+        O.ddp_solve_batch("cartpole", p, cfg, x0, u_init, native=native, outputs=False, nthreads=threads)
         done += B
         el = time.perf_counter() - t0
         if el >= min_seconds:
@@ -142,12 +151,12 @@ def run_reference(args, rank, world):
     sample = min(B, args.ref_sample)
     x0 = O.cartpole_x0(B, args.seed)[:sample]
     u_init = np.zeros((sample, N_STEPS, NU))
-    threads = O.lib(True).oracle_num_threads()
+    threads = host_threads()
     for _ in range(max(args.warmup, 1)):
-        O.ddp_solve_batch("cartpole", p, cfg, x0, u_init, native=True, outputs=False)
+        O.ddp_solve_batch("cartpole", p, cfg, x0, u_init, native=True, outputs=False, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.ddp_solve_batch("cartpole", p, cfg, x0, u_init, native=True, outputs=False)
+        O.ddp_solve_batch("cartpole", p, cfg, x0, u_init, native=True, outputs=False, nthreads=threads)
     el = time.perf_counter() - t0
     value = sample * args.steps / el
     line = {

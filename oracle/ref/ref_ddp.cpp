@@ -1,0 +1,172 @@
+// TEST INFRASTRUCTURE ONLY -- builds oracle/_ref/libnmpc_ref.so: the REFERENCE's own solver headers
+// (straight from /root/reference, unmodified) compiled against oracle/ref/eigen_shim, with the problem
+// classes of the reference's tests restated in the tests' own Eigen idioms (ref_models.h).  Used to pin
+// oracle/ (the plain restatement) against the reference's real control flow, and to generate
+// tests/golden/*.npz.  DDPSolver.hpp and FmpcSolver.hpp each define calcDuration() in an anonymous
+// namespace, so the two solvers live in separate translation units.
+#include <array>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <memory>
+#include <string>
+
+#include <nmpc_ddp/BoxQP.h>
+#include <nmpc_ddp/DDPSolver.h>
+
+#include "ref_models.h"
+
+namespace
+{
+using DDPProblemCartPole = CartPoleBodies<nmpc_ddp::DDPProblem<4, 1>>;
+}
+
+extern "C"
+{
+// same struct layouts as oracle/capi.cpp
+typedef struct
+{
+  int horizon_steps, max_iter, reg_type, with_input_constraint, n_alpha, reserved;
+  double initial_lambda, initial_dlambda, lambda_factor, lambda_min, lambda_max, k_rel_norm_thre, lambda_thre,
+      cost_update_ratio_thre, cost_update_thre;
+  double alpha_list[16];
+} ref_ddp_config;
+
+/** The reference's default Configuration, as its own constructor builds it (DDPSolver.h:47-110). */
+void ref_ddp_config_default(ref_ddp_config * cfg)
+{
+  nmpc_ddp::DDPSolver<4, 1>::Configuration c;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->horizon_steps = c.horizon_steps;
+  cfg->max_iter = c.max_iter;
+  cfg->reg_type = c.reg_type;
+  cfg->with_input_constraint = c.with_input_constraint;
+  cfg->n_alpha = c.alpha_list.size();
+  cfg->initial_lambda = c.initial_lambda;
+  cfg->initial_dlambda = c.initial_dlambda;
+  cfg->lambda_factor = c.lambda_factor;
+  cfg->lambda_min = c.lambda_min;
+  cfg->lambda_max = c.lambda_max;
+  cfg->k_rel_norm_thre = c.k_rel_norm_thre;
+  cfg->lambda_thre = c.lambda_thre;
+  cfg->cost_update_ratio_thre = c.cost_update_ratio_thre;
+  cfg->cost_update_thre = c.cost_update_thre;
+  for(int i = 0; i < cfg->n_alpha; i++) cfg->alpha_list[i] = c.alpha_list[i];
+}
+
+/** One cart-pole DDPSolver::solve() with the reference's code.  Arrays as in oracle_ddp_solve_batch, B = 1. */
+int ref_ddp_solve_cartpole(const double * params,
+                           const ref_ddp_config * cfg,
+                           double t0,
+                           const double * x0,
+                           const double * u_init,
+                           const double * u_lo,
+                           const double * u_hi,
+                           double * x_out,
+                           double * u_out,
+                           double * cost_out,
+                           double * trace_out,
+                           int * n_trace_out,
+                           int * solve_ret)
+{
+  auto problem = std::make_shared<DDPProblemCartPole>(params);
+  nmpc_ddp::DDPSolver<4, 1> solver(problem);
+  auto & c = solver.config();
+  c.print_level = 0;
+  c.with_input_constraint = cfg->with_input_constraint != 0;
+  c.max_iter = cfg->max_iter;
+  c.horizon_steps = cfg->horizon_steps;
+  c.reg_type = cfg->reg_type;
+  c.initial_lambda = cfg->initial_lambda;
+  c.initial_dlambda = cfg->initial_dlambda;
+  c.lambda_factor = cfg->lambda_factor;
+  c.lambda_min = cfg->lambda_min;
+  c.lambda_max = cfg->lambda_max;
+  c.k_rel_norm_thre = cfg->k_rel_norm_thre;
+  c.lambda_thre = cfg->lambda_thre;
+  c.alpha_list.resize(cfg->n_alpha);
+  for(int i = 0; i < cfg->n_alpha; i++) c.alpha_list[i] = cfg->alpha_list[i];
+  c.cost_update_ratio_thre = cfg->cost_update_ratio_thre;
+  c.cost_update_thre = cfg->cost_update_thre;
+  if(c.with_input_constraint)
+  {
+    const double lo = u_lo[0], hi = u_hi[0];
+    solver.setInputLimitsFunc([lo, hi](double) {
+      std::array<DDPProblemCartPole::InputDimVector, 2> limits;
+      limits[0].setConstant(lo);
+      limits[1].setConstant(hi);
+      return limits;
+    });
+  }
+  const int N = cfg->horizon_steps;
+  DDPProblemCartPole::StateDimVector current_x;
+  current_x << x0[0], x0[1], x0[2], x0[3];
+  std::vector<DDPProblemCartPole::InputDimVector> initial_u_list(N);
+  for(int i = 0; i < N; i++) initial_u_list[i][0] = u_init[i];
+  // the unconstrained branch prints "[DDP/Forward] Value is not expected to decrease." even at print_level 0
+  std::streambuf * old = std::cout.rdbuf(nullptr);
+  bool ret = false;
+  try
+  {
+    ret = solver.solve(t0, current_x, initial_u_list);
+  }
+  catch(...)
+  {
+    std::cout.rdbuf(old);
+    return -1;
+  }
+  std::cout.rdbuf(old);
+  *solve_ret = ret ? 1 : 0;
+  const auto & cd = solver.controlData();
+  for(int i = 0; i <= N; i++)
+  {
+    for(int d = 0; d < 4; d++) x_out[i * 4 + d] = cd.x_list[i][d];
+    cost_out[i] = cd.cost_list[i];
+  }
+  for(int i = 0; i < N; i++) u_out[i] = cd.u_list[i][0];
+  const auto & tl = solver.traceDataList();
+  std::memset(trace_out, 0, sizeof(double) * (cfg->max_iter + 1) * 9);
+  for(size_t r = 0; r < tl.size(); r++)
+  {
+    double * tr = trace_out + r * 9;
+    tr[0] = tl[r].iter, tr[1] = tl[r].cost, tr[2] = tl[r].lambda, tr[3] = tl[r].dlambda, tr[4] = tl[r].alpha;
+    tr[5] = tl[r].k_rel_norm, tr[6] = tl[r].cost_update_actual, tr[7] = tl[r].cost_update_expected;
+    tr[8] = tl[r].cost_update_ratio;
+  }
+  *n_trace_out = (int)tl.size();
+  return 0;
+}
+
+/** nmpc_ddp::BoxQP<2>::solve / BoxQP<Dynamic>::solve with the reference's code (TestBoxQP.cpp cases). */
+int ref_boxqp_solve2(const double * H, const double * g, const double * lower, const double * upper, int dynamic,
+                     double * x_out, int * retval)
+{
+  std::streambuf * old = std::cout.rdbuf(nullptr);
+  if(dynamic)
+  {
+    nmpc_ddp::BoxQP<Eigen::Dynamic> qp(2);
+    Eigen::MatrixXd Hm(2, 2);
+    Eigen::VectorXd gv(2), lo(2), up(2);
+    for(int j = 0; j < 2; j++)
+      for(int i = 0; i < 2; i++) Hm(i, j) = H[i + 2 * j];
+    for(int i = 0; i < 2; i++) gv[i] = g[i], lo[i] = lower[i], up[i] = upper[i];
+    Eigen::VectorXd x = qp.solve(Hm, gv, lo, up);
+    x_out[0] = x[0], x_out[1] = x[1];
+    *retval = qp.retval_;
+  }
+  else
+  {
+    nmpc_ddp::BoxQP<2> qp;
+    Eigen::Matrix2d Hm;
+    Eigen::Vector2d gv, lo, up;
+    for(int j = 0; j < 2; j++)
+      for(int i = 0; i < 2; i++) Hm(i, j) = H[i + 2 * j];
+    for(int i = 0; i < 2; i++) gv[i] = g[i], lo[i] = lower[i], up[i] = upper[i];
+    Eigen::Vector2d x = qp.solve(Hm, gv, lo, up);
+    x_out[0] = x[0], x_out[1] = x[1];
+    *retval = qp.retval_;
+  }
+  std::cout.rdbuf(old);
+  return 0;
+}
+} // extern "C"

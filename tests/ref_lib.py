@@ -1,0 +1,96 @@
+"""ctypes binding of oracle/_ref/libnmpc_ref.so: the REFERENCE's own DDPSolver / BoxQP / FmpcSolver headers
+compiled (unmodified, from /root/reference) against the Eigen-subset shim of oracle/ref/eigen_shim.
+
+TEST INFRASTRUCTURE.  Exists only where /root/reference does (the build container); everywhere else the
+vectors it produced are read from tests/golden/reference_outputs.npz."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import oracle_lib as O
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_REF_DIR = os.path.join(_ROOT, "oracle", "ref")
+_LIB = os.path.join(_ROOT, "oracle", "_ref", "libnmpc_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
+
+def available():
+    return os.path.isdir(REFERENCE_ROOT)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("the reference checkout is not present on this machine")
+        subprocess.run(["make", "-s", "-C", _REF_DIR], check=True)
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def ddp_config(**kw):
+    """The reference's own default Configuration (built by its constructor), then overrides."""
+    cfg = O.DdpConfig()
+    lib().ref_ddp_config_default(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def ddp_solve_cartpole(params, cfg, x0, u_init, t0=0.0, u_lo=None, u_hi=None):
+    N = cfg.horizon_steps
+    x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(4)
+    u_init = np.ascontiguousarray(u_init, dtype=np.float64).reshape(N)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    out = {"x": np.zeros((N + 1, 4)), "u": np.zeros((N, 1)), "cost_list": np.zeros(N + 1),
+           "trace": np.zeros((cfg.max_iter + 1, 9))}
+    n_trace, ret = C.c_int(), C.c_int()
+    lo = None if u_lo is None else np.ascontiguousarray(u_lo, dtype=np.float64)
+    hi = None if u_hi is None else np.ascontiguousarray(u_hi, dtype=np.float64)
+    rc = lib().ref_ddp_solve_cartpole(_p(params), C.byref(cfg), C.c_double(t0), _p(x0), _p(u_init), _p(lo), _p(hi),
+                                      _p(out["x"]), _p(out["u"]), _p(out["cost_list"]), _p(out["trace"]),
+                                      C.byref(n_trace), C.byref(ret))
+    if rc != 0:
+        raise RuntimeError("reference DDPSolver::solve threw")
+    out["n_trace"], out["solve_ret"] = n_trace.value, ret.value
+    return out
+
+
+def fmpc_solve(model, params, cfg, x0, var, t0=0.0):
+    nx, nu, ng, _ = O.model_dims(model)
+    N = cfg.horizon_steps
+    x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(nx)
+    vin = {k: np.ascontiguousarray(var[k], dtype=np.float64) for k in ("x", "u", "lambda", "s", "nu")}
+    out = {"x": np.zeros((N + 1, nx)), "u": np.zeros((N, nu)), "lambda": np.zeros((N + 1, nx)),
+           "s": np.zeros((N, ng)), "nu": np.zeros((N, ng)), "K": np.zeros((N, nu * nx)),
+           "kkt": np.zeros(max(cfg.max_iter, 1))}
+    n_trace, status = C.c_int(), C.c_int()
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    rc = lib().ref_fmpc_solve(model.encode(), _p(params), C.byref(cfg), C.c_double(t0), _p(x0), _p(vin["x"]),
+                              _p(vin["u"]), _p(vin["lambda"]), _p(vin["s"]), _p(vin["nu"]), _p(out["x"]),
+                              _p(out["u"]), _p(out["lambda"]), _p(out["s"]), _p(out["nu"]), _p(out["K"]),
+                              _p(out["kkt"]), C.byref(n_trace), C.byref(status))
+    if rc != 0:
+        raise RuntimeError("reference FmpcSolver::solve threw")
+    out["n_trace"], out["status"] = n_trace.value, status.value
+    return out
+
+
+def boxqp_solve2(H, g, lower, upper, dynamic):
+    Hc = np.asfortranarray(np.asarray(H, dtype=np.float64)).ravel(order="F").copy()
+    g, lower, upper = (np.ascontiguousarray(v, dtype=np.float64) for v in (g, lower, upper))
+    x = np.zeros(2)
+    retval = C.c_int()
+    assert lib().ref_boxqp_solve2(_p(Hc), _p(g), _p(lower), _p(upper), C.c_int(int(dynamic)), _p(x),
+                                  C.byref(retval)) == 0
+    return x, retval.value
