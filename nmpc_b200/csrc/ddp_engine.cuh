@@ -9,6 +9,7 @@
  */
 #pragma once
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -62,9 +63,9 @@ public:
     u_lo_.assign(NU, 0.0);
     u_hi_.assign(NU, 0.0);
     NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)backwardSmemBytes(kMaxThreadsPerBlock)));
+                                         (int)backwardSmemBytes(maxThreadsPerBlock())));
     NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)backwardSmemBytes(kMaxThreadsPerBlock)));
+                                         (int)backwardSmemBytes(maxThreadsPerBlock())));
     applyConfig(cfg, true);
   }
 
@@ -445,6 +446,12 @@ protected:
     constexpr int ipw = 32 / GA;
     const int grid = (B + kWarps * ipw - 1) / (kWarps * ipw);
     const size_t smem = sizeof(S) * (size_t)kWarps * 4 * FwdOperands<NX, NU>::SIZE * ipw;
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      cudaFuncSetAttribute(forward_spec_kernel<M, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
     forward_spec_kernel<M, GA><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, iter);
   }
 
@@ -463,17 +470,26 @@ protected:
     }
   }
 
+  /** Largest CTA whose two-stage block ring fits the 227 KB of shared memory an SM offers. */
+  static int maxThreadsPerBlock()
+  {
+    int tpb = kMaxThreadsPerBlock;
+    while(tpb > 32 && backwardSmemBytes(tpb) > 200 * 1024) tpb -= 32;
+    return tpb;
+  }
+
   static int threadsPerBlock(int B)
   {
+    const int cap = maxThreadsPerBlock();
     if(const char * env = std::getenv("NMPC_B200_TPB"))
     {
       int v = std::atoi(env);
-      if(v >= 32 && v <= kMaxThreadsPerBlock && v % 32 == 0) return v;
+      if(v >= 32 && v <= cap && v % 32 == 0) return v;
     }
     // spread small batches over all 148 SMs: one warp per CTA until every SM has a few warps
     if(B <= 148 * 32 * 2) return 32;
-    if(B <= 148 * 64 * 4) return 64;
-    return 128;
+    if(B <= 148 * 64 * 4) return std::min(64, cap);
+    return std::min(128, cap);
   }
 
   void record(cudaStream_t st)

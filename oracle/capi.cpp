@@ -289,6 +289,11 @@ int oracle_model_dims(const char * model, int * nx, int * nu, int * ng, int * np
     *nx = 2, *nu = 1, *ng = 0, *nparams = DDPProblemBipedal::kNumParams;
     return 0;
   }
+  if(m == "quadrotor")
+  {
+    *nx = 12, *nu = 4, *ng = 0, *nparams = DDPProblemQuadrotor::kNumParams;
+    return 0;
+  }
   if(m == "fmpc_cartpole")
   {
     *nx = 4, *nu = 1, *ng = 4, *nparams = FmpcProblemCartPole::kNumParams;
@@ -309,6 +314,8 @@ int oracle_model_default_params(const char * model, double * params)
     DDPProblemCartPole::defaultParams(params);
   else if(m == "bipedal")
     DDPProblemBipedal::defaultParams(params);
+  else if(m == "quadrotor")
+    DDPProblemQuadrotor::defaultParams(params);
   else if(m == "fmpc_cartpole")
     FmpcProblemCartPole::defaultParams(params);
   else if(m == "fmpc_oscillator")
@@ -349,6 +356,10 @@ int oracle_ddp_solve_batch(const char * model,
     return ddpSolveBatch<DDPProblemBipedal, 2, 1>(params, cfg, B, t0, x0, u_init, u_lo, u_hi, x_out, u_out, cost_out,
                                                   k_out, K_out, trace_out, n_trace_out, status_out, iters_out,
                                                   n_fwd_out, n_bwd_out, nthreads);
+  if(m == "quadrotor")
+    return ddpSolveBatch<DDPProblemQuadrotor, 12, 4>(params, cfg, B, t0, x0, u_init, u_lo, u_hi, x_out, u_out,
+                                                     cost_out, k_out, K_out, trace_out, n_trace_out, status_out,
+                                                     iters_out, n_fwd_out, n_bwd_out, nthreads);
   return -2;
 }
 
@@ -374,6 +385,8 @@ int oracle_model_eval(const char * model,
     return modelEval<DDPProblemCartPole, 4, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
   if(m == "bipedal")
     return modelEval<DDPProblemBipedal, 2, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
+  if(m == "quadrotor")
+    return modelEval<DDPProblemQuadrotor, 12, 4>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
   if(m == "fmpc_cartpole")
     return modelEval<FmpcProblemCartPole, 4, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
   if(m == "fmpc_oscillator")

@@ -525,3 +525,107 @@ public:
   }
 };
 } // namespace oracle
+
+// ---- quadrotor (BASELINE.json configs[3]; no counterpart in the reference) ----
+// The functor of include/nmpc_b200/models/quadrotor.h instantiated in double is the fp64 reference for
+// the fp32 device run; the DDP *solver* around it is still the restatement of this directory.
+#include <nmpc_b200/models/quadrotor.h>
+
+namespace oracle
+{
+class DDPProblemQuadrotor : public DDPProblem<12, 4>
+{
+public:
+  using F = nmpc_b200::models::Quadrotor<double>;
+  static constexpr int kNumParams = F::NUM_PARAMS;
+
+  explicit DDPProblemQuadrotor(const double * p) : DDPProblem<12, 4>(p[0]), f_(F::fromParams(p)) {}
+  static void defaultParams(double * p)
+  {
+    F::defaultParams(p);
+  }
+
+  template<class A, class B>
+  static void copy(const A & a, B & b, int n)
+  {
+    for(int i = 0; i < n; i++) b.d[i] = a.d[i];
+  }
+  StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    F::StateDimVector fx, fn;
+    F::InputDimVector fu;
+    copy(x, fx, 12);
+    copy(u, fu, 4);
+    fn = f_.stateEq(t, fx, fu);
+    StateDimVector out;
+    copy(fn, out, 12);
+    return out;
+  }
+  double runningCost(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    F::StateDimVector fx;
+    F::InputDimVector fu;
+    copy(x, fx, 12);
+    copy(u, fu, 4);
+    return f_.runningCost(t, fx, fu);
+  }
+  double terminalCost(double t, const StateDimVector & x) const override
+  {
+    F::StateDimVector fx;
+    copy(x, fx, 12);
+    return f_.terminalCost(t, fx);
+  }
+  void calcStateEqDeriv(double t,
+                        const StateDimVector & x,
+                        const InputDimVector & u,
+                        StateStateDimMatrix & Fx,
+                        StateInputDimMatrix & Fu) const override
+  {
+    F::StateDimVector fx;
+    F::InputDimVector fu;
+    F::StateStateDimMatrix a;
+    F::StateInputDimMatrix b;
+    copy(x, fx, 12);
+    copy(u, fu, 4);
+    f_.calcStateEqDeriv(t, fx, fu, a, b);
+    copy(a, Fx, 144);
+    copy(b, Fu, 48);
+  }
+  void calcRunningCostDeriv(double t,
+                            const StateDimVector & x,
+                            const InputDimVector & u,
+                            StateDimVector & Lx,
+                            InputDimVector & Lu,
+                            StateStateDimMatrix & Lxx,
+                            InputInputDimMatrix & Luu,
+                            StateInputDimMatrix & Lxu) const override
+  {
+    F::StateDimVector fx, lx;
+    F::InputDimVector fu, lu;
+    F::StateStateDimMatrix lxx;
+    F::InputInputDimMatrix luu;
+    F::StateInputDimMatrix lxu;
+    copy(x, fx, 12);
+    copy(u, fu, 4);
+    f_.calcRunningCostDeriv(t, fx, fu, lx, lu, lxx, luu, lxu);
+    copy(lx, Lx, 12);
+    copy(lu, Lu, 4);
+    copy(lxx, Lxx, 144);
+    copy(luu, Luu, 16);
+    copy(lxu, Lxu, 48);
+  }
+  void calcTerminalCostDeriv(double t, const StateDimVector & x, StateDimVector & Vx, StateStateDimMatrix & Vxx)
+      const override
+  {
+    F::StateDimVector fx, vx;
+    F::StateStateDimMatrix vxx;
+    copy(x, fx, 12);
+    f_.calcTerminalCostDeriv(t, fx, vx, vxx);
+    copy(vx, Vx, 12);
+    copy(vxx, Vxx, 144);
+  }
+
+protected:
+  F f_;
+};
+} // namespace oracle
