@@ -78,7 +78,7 @@ __device__ __forceinline__ bool backwardSweepCoop(const Workspace<typename M::Sc
         const int e = e0 + j;
         if(e < C::STAGE)
         {
-          const S * src = (e < L::SIZE) ? ws.deriv + ((size_t)step * L::SIZE + e) * Bp + b
+          const S * src = (e < L::SIZE) ? ws.deriv + derivTileOffset<L::SIZE>(step, b, ws.Bp) + (size_t)e * kTile
                                         : us + ((size_t)step * NU + (e - L::SIZE)) * Bp + b;
           S * dst = &at(C::RING + stage * C::STAGE, e);
           if constexpr(sizeof(S) == 8)

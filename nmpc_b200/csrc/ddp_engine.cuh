@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "ddp_kernels.cuh"
 #include "ddp_backward_coop.cuh"
+#include "ddp_forward_phased.cuh"
 #include "registry.h"
 
 namespace nmpc_b200
@@ -371,13 +372,14 @@ public:
 protected:
   static constexpr int kMaxThreadsPerBlock = 128;
   static constexpr bool kHasBoxQP = true;
+  static constexpr int kPhased = 3; //!< K3 variant id: three-phase line search
   // group size of the cooperative K2: the power of two >= NX, capped at a warp
   static constexpr int kCoopGS = (NX <= 1) ? 1 : (NX <= 2) ? 2 : (NX <= 4) ? 4 : (NX <= 8) ? 8 : (NX <= 16) ? 16 : 32;
 
   /** K2 stages two derivative blocks per thread in shared memory (cp.async ring). */
   static size_t backwardSmemBytes(int tpb)
   {
-    return 2 * sizeof(S) * (size_t)(L::SIZE + NU) * tpb;
+    return 2 * sizeof(S) * (size_t)L::SIZE * tpb + 16 * (size_t)(tpb / 32) + 128;
   }
 
   /** K3 variant: lanes per instance that evaluate line-search candidates concurrently.  Small
@@ -387,10 +389,9 @@ protected:
     if(const char * env = std::getenv("NMPC_B200_FWD_GA"))
     {
       int v = std::atoi(env);
-      if(v == 1 || v == 4 || v == 16) return v;
+      if(v == 1 || v == 4 || v == 16 || v == kPhased) return v;
     }
-    if(B <= 148 * 32) return 16; // <= 16 warps per SM
-    if(B <= 148 * 128) return 4;
+    if(B <= 148 * 128) return kPhased; // latency-bound regime: minimise the number of sequential rollouts
     return 1;
   }
 
@@ -402,7 +403,10 @@ protected:
       int v = std::atoi(env);
       if(v == 1 || v == kCoopGS) return v;
     }
-    // cooperative groups pay off while one thread per instance cannot fill the warp schedulers
+    // One thread per instance keeps every matrix in registers and is the faster variant while they fit
+    // (measured on B200, cart-pole 4x1, B=4096: 84 us vs 113 us per sweep).  From n_x = 8 on the register
+    // file overflows (n_x = 12: 19 KB of spills per thread) and the cooperative variant takes over.
+    if(NX < 8) return 1;
     return (B <= 148 * 128) ? kCoopGS : 1;
   }
 
@@ -455,6 +459,52 @@ protected:
     forward_spec_kernel<M, GA><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, iter);
   }
 
+  /** Three-phase line search (ddp_forward_phased.cuh). */
+  void launchForwardPhased(int B, int iter, cudaStream_t st)
+  {
+    using O = FwdOperands<NX, NU>;
+    ensureFanout();
+    {
+      constexpr int kWarps = 1; // one warp per CTA spreads 4096 instances over 128 SMs
+      const size_t smem = sizeof(S) * (size_t)kWarps * 4 * O::SIZE * 32;
+      static bool attr_set = false;
+      if(!attr_set)
+      {
+        cudaFuncSetAttribute(forward_first_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+      }
+      forward_first_kernel<M><<<(B + kWarps * 32 - 1) / (kWarps * 32), kWarps * 32, smem, st>>>(model_, ws_, prm_, fan_,
+                                                                                             iter);
+    }
+    {
+      constexpr int kWarps = 4;
+      constexpr int ipw = 32 / kFanLanes;
+      const size_t smem = sizeof(S) * (size_t)kWarps * 4 * O::SIZE * ipw;
+      const int grid = (B + kWarps * ipw - 1) / (kWarps * ipw); // worst case: every instance listed
+      forward_fanout_kernel<M><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, fan_, iter);
+    }
+    {
+      const dim3 block(32, 16), grid((B + 31) / 32, 8);
+      forward_commit_kernel<M><<<grid, block, 0, st>>>(ws_, prm_, fan_);
+    }
+  }
+
+  void ensureFanout()
+  {
+    const size_t N = cfg_.horizon_steps;
+    const size_t items = (size_t)Bp_ * kFanLanes;
+    if(fan_.items == items && fan_scratch_.count == items * ((N + 1) * NX + N * NU + (N + 1))) return;
+    fan_scratch_.allocate(items * ((N + 1) * NX + N * NU + (N + 1)));
+    fan_ints_.allocate(2 * (size_t)Bp_);
+    fan_.count = d_fan_count_.ptr;
+    fan_.list = fan_ints_.ptr;
+    fan_.commit_item = fan_ints_.ptr + Bp_;
+    fan_.sx = fan_scratch_.ptr;
+    fan_.su = fan_.sx + items * (N + 1) * NX;
+    fan_.sc = fan_.su + items * N * NU;
+    fan_.items = items;
+  }
+
   void launchForward(int B, int tpb, int grid, int iter, cudaStream_t st)
   {
     switch(forwardLanesPerInstance(B))
@@ -464,6 +514,9 @@ protected:
         break;
       case 4:
         launchForwardSpec<4>(B, iter, st);
+        break;
+      case kPhased:
+        launchForwardPhased(B, iter, st);
         break;
       default:
         forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
@@ -563,6 +616,11 @@ protected:
     d_u_lo_.allocate(NU > 0 ? NU : 1);
     d_u_hi_.allocate(NU > 0 ? NU : 1);
     d_counter_.allocate(1);
+    d_fan_count_.allocate(1);
+    NMPC_CUDA_CHECK(cudaMemset(d_fan_count_.ptr, 0, sizeof(int)));
+    ws_.fan_count = d_fan_count_.ptr;
+    fan_ = FwdFanout<S>{};
+    fan_scratch_.release();
     stage_in_x_.allocate((size_t)capacity_ * NX);
     stage_in_u_.allocate((size_t)capacity_ * N * NU);
     NMPC_CUDA_CHECK(cudaMemset(scal_.ptr, 0, scal_.bytes()));
@@ -600,7 +658,9 @@ protected:
   cudaStream_t own_stream_ = nullptr;
   cudaStream_t last_stream_ = nullptr;
   DeviceBuffer<S> x_[2], u_[2], cost_[2], deriv_, vterm_, kff_, kfb_, trace_, scal_, d_u_lo_, d_u_hi_;
-  DeviceBuffer<int> ints_, d_counter_;
+  DeviceBuffer<int> ints_, d_counter_, d_fan_count_, fan_ints_;
+  DeviceBuffer<S> fan_scratch_;
+  FwdFanout<S> fan_{};
   DeviceBuffer<double> stage_in_x_, stage_in_u_, stage_out_;
   int * h_counter_ = nullptr;
   std::vector<double> u_lo_, u_hi_;

@@ -1,0 +1,218 @@
+/* nmpc_b200 -- K3 for small batches, in three phases (procOnce() Steps 3-4, DDPSolver.hpp:234-339).
+ *
+ * At 4096 instances the line search is bound by the latency of one rollout (100 dependent steps of
+ * sincos -> reciprocal -> state update), not by throughput, so the number of SEQUENTIAL rollouts per
+ * iteration is what matters:
+ *
+ *   phase 1  forward_first_kernel    every instance rolls out alpha_list[0] (one thread each, operands fed
+ *                                    by a 4-deep cp.async ring) and stores the candidate; ~90 % of all line
+ *                                    searches end here.  Instances whose first candidate fails are
+ *                                    appended to a work list.
+ *   phase 2  forward_fanout_kernel   ALL remaining candidates of ALL listed instances are rolled out
+ *                                    concurrently, one lane per (instance, candidate), 16 lanes per
+ *                                    instance sharing one operand ring; each lane writes its trajectory
+ *                                    to scratch.  First success in list order wins -- identical to the
+ *                                    reference's sequential backtracking because forwardPass(alpha) is a
+ *                                    pure function of alpha.
+ *   phase 3  forward_commit_kernel   the winners' scratch trajectories are copied into the (new) current
+ *                                    buffer.
+ *
+ * A late M-fixed iteration therefore costs two rollout latencies instead of up to eleven.
+ */
+#pragma once
+
+#include "ddp_kernels.cuh"
+
+namespace nmpc_b200
+{
+namespace ddp
+{
+constexpr int kFanLanes = 16; //!< lanes (candidate slots) per listed instance in phase 2
+
+template<class S>
+struct FwdFanout
+{
+  int * count; //!< [1] number of listed instances (reset by K1 / K0)
+  int * list; //!< [Bp] instance index per slot
+  int * commit_item; //!< [Bp] per slot: scratch column of the winning candidate, or -1
+  S * sx; //!< scratch candidates [N+1][NX][items]
+  S * su; //!< [N][NU][items]
+  S * sc; //!< [N+1][items]
+  size_t items; //!< scratch columns = Bp * kFanLanes
+};
+
+/** procOnce() Step 4 (DDPSolver.hpp:280-339) for one instance, after its line search is decided. */
+template<class S>
+__device__ __forceinline__ void lineSearchFinish(const Workspace<S> & ws,
+                                                 const SolverParams<S> & prm,
+                                                 int b,
+                                                 int iter,
+                                                 int sel,
+                                                 bool success,
+                                                 S alpha,
+                                                 S actual,
+                                                 S expected,
+                                                 S ratio,
+                                                 S cost_cur,
+                                                 S cost_new,
+                                                 int tried)
+{
+  S lambda = ws.lambda[b];
+  S dlambda = ws.dlambda[b];
+  const S k_rel_norm = ws.trace[((size_t)iter * kTraceFields + 5) * ws.Bp + b];
+  int retval = 0;
+  S cost_out = cost_cur;
+  if(success)
+  {
+    ws.sel[b] = sel ^ 1;
+    ws.cost_sum[b] = cost_new;
+    cost_out = cost_new;
+    if(actual < prm.cost_update_thre) retval = 1;
+    dlambda = fmin(dlambda / prm.lambda_factor, S(1) / prm.lambda_factor);
+    if(lambda >= prm.lambda_min)
+      lambda *= dlambda;
+    else
+      lambda = S(0);
+  }
+  else
+  {
+    dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
+    lambda = fmax(lambda * dlambda, prm.lambda_min);
+    if(lambda > prm.lambda_max) retval = -1;
+  }
+  ws.lambda[b] = lambda;
+  ws.dlambda[b] = dlambda;
+  ws.n_fwd[b] += tried;
+  ws.iters[b] = iter;
+  if(retval != 0) ws.status[b] = retval;
+  writeTrace<S>(ws, b, iter, S(iter), cost_out, lambda, dlambda, alpha, k_rel_norm, actual, expected, ratio);
+}
+
+/** Phase 1: alpha_list[0] for every running instance. */
+template<class M>
+__global__ void forward_first_kernel(const __grid_constant__ M model,
+                                     const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                     const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                     const __grid_constant__ FwdFanout<typename M::Scalar> fan,
+                                     int iter)
+{
+  using S = typename M::Scalar;
+  constexpr int DEPTH = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  S * ring = reinterpret_cast<S *>(smem_raw) + (size_t)warp * DEPTH * FwdOperands<M::NX, M::NU>::SIZE * 32;
+
+  const int bg = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (bg < ws.B) ? bg : (ws.B - 1);
+  const bool active = (bg < ws.B) && (ws.status[b] == 0);
+  const int sel = ws.sel[b];
+  const bool work = active && prm.n_alpha > 0;
+  const S alpha = prm.alpha_list[0];
+  const S cost_new =
+      forwardRolloutRing<M, 1, DEPTH>(model, ws, prm, ring, lane, 0, b, sel, alpha, work, work, work,
+                                      candidateBuffer<S>(ws, sel, b));
+  if(!active) return;
+  const S cost_cur = ws.cost_sum[b];
+  S actual = S(0), expected = S(0), ratio = S(0);
+  bool success = false;
+  if(work) success = lineSearchTest<S>(prm, cost_cur, cost_new, alpha, ws.dV[b], ws.dV[(size_t)ws.Bp + b], actual,
+                                       expected, ratio);
+  if(success || prm.n_alpha <= 1)
+  {
+    lineSearchFinish<S>(ws, prm, b, iter, sel, success, work ? alpha : S(0), actual, expected, ratio, cost_cur,
+                        cost_new, work ? 1 : 0);
+    return;
+  }
+  const int slot = atomicAdd(fan.count, 1);
+  fan.list[slot] = b;
+}
+
+/** Phase 2: candidates 1 .. n_alpha-1 of every listed instance at once. */
+template<class M>
+__global__ void forward_fanout_kernel(const __grid_constant__ M model,
+                                      const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                      const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                      const __grid_constant__ FwdFanout<typename M::Scalar> fan,
+                                      int iter)
+{
+  using S = typename M::Scalar;
+  constexpr int GA = kFanLanes;
+  constexpr int IPW = 32 / GA;
+  constexpr int DEPTH = 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr unsigned kGroupMask = (1u << GA) - 1u;
+  const int count = *fan.count;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp_slot0 = (blockIdx.x * (blockDim.x >> 5) + warp) * IPW;
+  if(warp_slot0 >= count) return; // warp-uniform
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S * ring = reinterpret_cast<S *>(smem_raw) + (size_t)warp * DEPTH * FwdOperands<M::NX, M::NU>::SIZE * IPW;
+
+  const int g = lane / GA;
+  const int a = lane % GA;
+  const int slot = warp_slot0 + g;
+  const bool valid = slot < count;
+  const int b = valid ? fan.list[slot] : fan.list[warp_slot0];
+  const int sel = ws.sel[b];
+  const int rem = prm.n_alpha - 1;
+  const bool work = valid && (a < rem);
+  const S my_alpha = prm.alpha_list[work ? (1 + a) : 0];
+  const size_t item = (size_t)slot * GA + a;
+  const FwdDest<S> dst{fan.sx, fan.su, fan.sc, fan.items, item};
+  const S my_cost = forwardRolloutRing<M, GA, DEPTH>(model, ws, prm, ring, g, a, b, sel, my_alpha, work, work, valid, dst);
+
+  const S cost_cur = ws.cost_sum[b];
+  S my_actual = S(0), my_expected = S(0), my_ratio = S(0);
+  bool ok = false;
+  if(work)
+    ok = lineSearchTest<S>(prm, cost_cur, my_cost, my_alpha, ws.dV[b], ws.dV[(size_t)ws.Bp + b], my_actual, my_expected,
+                           my_ratio);
+  const unsigned ok_ballot = __ballot_sync(kFull, ok);
+  const unsigned gm = (ok_ballot >> (g * GA)) & kGroupMask;
+  const int pick = (gm != 0) ? (__ffs(gm) - 1) : (rem - 1); // first success, else the last candidate tried
+  const int src = g * GA + pick;
+  const S r_actual = __shfl_sync(kFull, my_actual, src);
+  const S r_expected = __shfl_sync(kFull, my_expected, src);
+  const S r_ratio = __shfl_sync(kFull, my_ratio, src);
+  const S r_cost = __shfl_sync(kFull, my_cost, src);
+  const S r_alpha = __shfl_sync(kFull, my_alpha, src);
+  if(!valid || a != 0) return;
+  const bool success = gm != 0;
+  fan.commit_item[slot] = success ? (int)((size_t)slot * GA + pick) : -1;
+  lineSearchFinish<S>(ws, prm, b, iter, sel, success, r_alpha, r_actual, r_expected, r_ratio, cost_cur, r_cost,
+                      success ? (2 + pick) : prm.n_alpha);
+}
+
+/** Phase 3: copy each winner's scratch trajectory into its instance's new current buffer. */
+template<class M>
+__global__ void forward_commit_kernel(const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                      const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                      const __grid_constant__ FwdFanout<typename M::Scalar> fan)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  const int count = *fan.count;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if(blockIdx.x * blockDim.x >= count) return;
+  if(slot >= count) return;
+  const int item = fan.commit_item[slot];
+  if(item < 0) return;
+  const int b = fan.list[slot];
+  const int sel = ws.sel[b]; // already flipped by lineSearchFinish: the accepted trajectory lives here
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  const int rows_x = (N + 1) * NX, rows_u = N * NU, rows_c = N + 1;
+  for(int r = threadIdx.y + blockIdx.y * blockDim.y; r < rows_x + rows_u + rows_c; r += blockDim.y * gridDim.y)
+  {
+    if(r < rows_x)
+      ws.x[sel][(size_t)r * Bp + b] = fan.sx[(size_t)r * fan.items + item];
+    else if(r < rows_x + rows_u)
+      ws.u[sel][(size_t)(r - rows_x) * Bp + b] = fan.su[(size_t)(r - rows_x) * fan.items + item];
+    else
+      ws.cost[sel][(size_t)(r - rows_x - rows_u) * Bp + b] = fan.sc[(size_t)(r - rows_x - rows_u) * fan.items + item];
+  }
+}
+} // namespace ddp
+} // namespace nmpc_b200

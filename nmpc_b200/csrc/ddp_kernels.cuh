@@ -82,6 +82,7 @@ struct Workspace
   int * iters;
   int * n_fwd;
   int * n_bwd;
+  int * fan_count; //!< [1] work-list length of the phased line search (reset by K0 / K1)
 };
 
 template<int NX, int NU>
@@ -138,6 +139,50 @@ __device__ __forceinline__ void stageBlock(S * stage, const S * __restrict__ blk
   }
 }
 
+/* The derivative blocks are tiled by warp: [step][tile of 32 instances][BLK][32].  One warp's block of one
+   step is a single contiguous BLK * 32 * sizeof(S) chunk, so K2 fetches it with ONE bulk (TMA) copy. */
+constexpr int kTile = 32;
+
+template<int SIZE>
+__device__ __forceinline__ size_t derivTileOffset(int step, int b, int Bp)
+{
+  return ((size_t)step * (Bp / kTile) + (size_t)(b / kTile)) * SIZE * kTile + (size_t)(b % kTile);
+}
+
+__device__ __forceinline__ void mbarInit(unsigned long long * bar, unsigned count)
+{
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long * bar, unsigned bytes)
+{
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long * bar, unsigned parity)
+{
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_LOOP:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra WAIT_DONE;\n"
+               "bra WAIT_LOOP;\n"
+               "WAIT_DONE:\n"
+               "}\n" ::"r"(a),
+               "r"(parity)
+               : "memory");
+}
+/** One-dimensional bulk copy global -> shared through the TMA engine; completion lands on `bar`. */
+__device__ __forceinline__ void bulkCopyG2S(void * smem_dst, const void * gmem_src, unsigned bytes, unsigned long long * bar)
+{
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+               "l"(gmem_src), "r"(bytes), "r"(b)
+               : "memory");
+}
+
 template<class S>
 __device__ __forceinline__ void writeTrace(const Workspace<S> & ws,
                                            int b,
@@ -175,6 +220,7 @@ __global__ void rollout_init_kernel(const __grid_constant__ M model,
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b == 0) *ws.fan_count = 0;
   if(b >= ws.B) return;
   const size_t Bp = ws.Bp;
   const int N = prm.N;
@@ -228,6 +274,7 @@ __global__ void linearize_kernel(const __grid_constant__ M model,
   using L = BlockLayout<NX, NU>;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
+  if(b == 0 && i == 0) *ws.fan_count = 0; // the previous iteration's line-search work list is consumed
   if(b >= ws.B) return;
   if(ws.status[b] != 0) return;
   const size_t Bp = ws.Bp;
@@ -264,21 +311,21 @@ __global__ void linearize_kernel(const __grid_constant__ M model,
   model.calcStateEqDeriv(t, x, u, Fx, Fu);
   model.calcRunningCostDeriv(t, x, u, Lx, Lu, Lxx, Luu, Lxu);
 
-  S * blk = ws.deriv + (size_t)i * L::SIZE * Bp + b;
+  S * blk = ws.deriv + derivTileOffset<L::SIZE>(i, b, ws.Bp);
 #pragma unroll
-  for(int d = 0; d < NX * NX; d++) blk[(size_t)(L::FX + d) * Bp] = Fx.d[d];
+  for(int d = 0; d < NX * NX; d++) blk[(L::FX + d) * kTile] = Fx.d[d];
 #pragma unroll
-  for(int d = 0; d < NX * NU; d++) blk[(size_t)(L::FU + d) * Bp] = Fu.d[d];
+  for(int d = 0; d < NX * NU; d++) blk[(L::FU + d) * kTile] = Fu.d[d];
 #pragma unroll
-  for(int d = 0; d < NX; d++) blk[(size_t)(L::LX + d) * Bp] = Lx.d[d];
+  for(int d = 0; d < NX; d++) blk[(L::LX + d) * kTile] = Lx.d[d];
 #pragma unroll
-  for(int d = 0; d < NU; d++) blk[(size_t)(L::LU + d) * Bp] = Lu.d[d];
+  for(int d = 0; d < NU; d++) blk[(L::LU + d) * kTile] = Lu.d[d];
 #pragma unroll
-  for(int d = 0; d < NX * NX; d++) blk[(size_t)(L::LXX + d) * Bp] = Lxx.d[d];
+  for(int d = 0; d < NX * NX; d++) blk[(L::LXX + d) * kTile] = Lxx.d[d];
 #pragma unroll
-  for(int d = 0; d < NU * NU; d++) blk[(size_t)(L::LUU + d) * Bp] = Luu.d[d];
+  for(int d = 0; d < NU * NU; d++) blk[(L::LUU + d) * kTile] = Luu.d[d];
 #pragma unroll
-  for(int d = 0; d < NX * NU; d++) blk[(size_t)(L::LXU + d) * Bp] = Lxu.d[d];
+  for(int d = 0; d < NX * NU; d++) blk[(L::LXU + d) * kTile] = Lxu.d[d];
 }
 
 /* ------------------------------------------------------------------------------------ K2 ---- */
@@ -332,15 +379,20 @@ __device__ __forceinline__ void lltSolveInPlace(const S * l, const S * invd, S *
   }
 }
 
-/** One backwardPass() sweep (DDPSolver.hpp:343-534) with regularisation `lambda`.  Returns false as
-    soon as the Cholesky factorisation of Quu_F fails at some step (LLT NumericalIssue, :500-508). */
+/** One backwardPass() sweep (DDPSolver.hpp:343-534) with regularisation `lambda`, one thread per instance.
+    All 32 lanes of the warp execute the loop (lane 0 drives the TMA ring, everyone waits on its mbarriers);
+    only lanes with `work` compute.  Returns false when the Cholesky factorisation of Quu_F failed at some
+    step (LLT NumericalIssue, :500-508) -- the caller then raises lambda and sweeps again. */
 template<class M, bool CONSTRAINED>
 __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar> & ws,
                                               const SolverParams<typename M::Scalar> & prm,
                                               int b,
+                                              int lane,
                                               const typename M::Scalar * __restrict__ us,
                                               typename M::Scalar * __restrict__ ring,
-                                              int tpb,
+                                              unsigned long long * bars,
+                                              unsigned & parity,
+                                              bool work,
                                               typename M::Scalar lambda,
                                               typename M::Scalar & dV0,
                                               typename M::Scalar & dV1,
@@ -349,6 +401,8 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
   using L = BlockLayout<NX, NU>;
+  constexpr int tpb = kTile; // element stride inside a staged tile
+  constexpr unsigned kStageBytes = (unsigned)(sizeof(S) * L::SIZE * kTile);
   const size_t Bp = ws.Bp;
   const int N = prm.N;
 
@@ -363,32 +417,46 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
   // max_i |k_i| / (|u_i| + 1) is tracked as a (numerator, denominator) pair and divided once
   S krn_num = S(0), krn_den = S(1);
 
-  // two-stage shared-memory ring, one column per thread: while step i computes, the block of step
-  // i-1 is already in flight (cp.async), so the dependent Riccati chain never waits on HBM
-  // (the u_i needed by the termination test ride along as NU extra ring entries)
-  constexpr int kStageElems = L::SIZE + NU;
-  S * const ring0 = ring + threadIdx.x;
-  S * const ring1 = ring0 + (size_t)kStageElems * tpb;
-  auto stageStep = [&](S * dst, int step) {
-    stageBlock<S, L::SIZE>(dst, ws.deriv + (size_t)step * L::SIZE * Bp + b, Bp, tpb);
-    stageBlock<S, NU>(dst + (size_t)L::SIZE * tpb, us + (size_t)step * NU * Bp + b, Bp, tpb);
-    cpAsyncCommit();
+  // Two-stage shared-memory ring per warp.  The tile of step i-1 is fetched by one bulk (TMA) copy while
+  // step i computes, so the dependent Riccati chain never waits on HBM and no address arithmetic is spent
+  // on the 46 block entries: they are read back with immediate-offset shared loads.
+  const S * const tile0 = ws.deriv + derivTileOffset<L::SIZE>(0, b - lane, ws.Bp); // this warp's tile, step 0
+  const size_t step_stride = (size_t)(ws.Bp / kTile) * L::SIZE * kTile;
+  auto stageStep = [&](int stage, int step) {
+    if(lane == 0)
+    {
+      mbarExpectTx(&bars[stage], kStageBytes);
+      bulkCopyG2S(ring + (size_t)stage * L::SIZE * kTile, tile0 + (size_t)step * step_stride, kStageBytes, &bars[stage]);
+    }
   };
-  stageStep(ring0, N - 1);
+  __syncwarp(); // the previous sweep's readers are done with the ring
+  stageStep(0, N - 1);
   int stage = 0;
   S k_prev[NU]; // k_list_[i + 1], the BoxQP warm start (:452-467)
 #pragma unroll
   for(int a = 0; a < NU; a++) k_prev[a] = S(0);
+  S u_cur[NU], u_nxt[NU]; // u_i for the termination test / input limits, fetched one step ahead
+#pragma unroll
+  for(int a = 0; a < NU; a++) u_cur[a] = us[((size_t)(N - 1) * NU + a) * Bp + b];
+  bool ok = true;
 
   for(int i = N - 1; i >= 0; i--)
   {
-    const S * const blk = stage ? ring1 : ring0;
-    if(i > 0)
-      stageStep(stage ? ring0 : ring1, i - 1);
-    else
-      cpAsyncCommit();
-    cpAsyncWait<1>();
+    const S * const blk = ring + (size_t)stage * L::SIZE * kTile + lane;
+    __syncwarp(); // every lane has finished reading the other stage (step i+1)
+    if(i > 0) stageStep(stage ^ 1, i - 1);
+    {
+      const int ip = (i > 0) ? i - 1 : 0;
+#pragma unroll
+      for(int a = 0; a < NU; a++) u_nxt[a] = us[((size_t)ip * NU + a) * Bp + b];
+    }
+    mbarWait(&bars[stage], (parity >> stage) & 1u);
+    parity ^= (1u << stage);
     stage ^= 1;
+    if(work && ok)
+    {
+      do
+      {
     S Fx[NX * NX], Fu[NX * NU];
 #pragma unroll
     for(int d = 0; d < NX * NX; d++) Fx[d] = blk[(size_t)(L::FX + d) * tpb];
@@ -524,7 +592,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
 #pragma unroll
       for(int a = 0; a < NU; a++)
       {
-        const S uv = blk[(size_t)(L::SIZE + a) * tpb];
+        const S uv = u_cur[a];
         lo[a] = ws.u_lo[a] - uv;
         hi[a] = ws.u_hi[a] - uv;
         init[a] = (i == N - 1) ? S(0) : k_prev[a];
@@ -533,8 +601,8 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
       boxQpSolve<S, NU>(Quu_F, Qu, lo, hi, init, qp);
       if(qp.retval < 0)
       {
-        cpAsyncWait<0>();
-        return false;
+        ok = false;
+        break;
       }
 #pragma unroll
       for(int a = 0; a < NU; a++) k[a] = qp.x[a];
@@ -565,8 +633,8 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
       // 1x1: the LLT failure rule is "Quu_F <= 0"; L L^T solve == one reciprocal
       if(Quu_F[0] <= S(0))
       {
-        cpAsyncWait<0>();
-        return false;
+        ok = false;
+        break;
       }
       const S inv = S(1) / Quu_F[0];
       k[0] = -(Qu[0] * inv);
@@ -577,8 +645,8 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
     {
       if(!lltInPlace<S, NU>(Quu_F))
       {
-        cpAsyncWait<0>();
-        return false;
+        ok = false;
+        break;
       }
       S invd[NU];
 #pragma unroll
@@ -679,7 +747,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
     {
       ws.kff[((size_t)i * NU + a) * Bp + b] = k[a];
       kn += k[a] * k[a];
-      const S uv = blk[(size_t)(L::SIZE + a) * tpb];
+      const S uv = u_cur[a];
       un += uv * uv;
     }
 #pragma unroll
@@ -687,20 +755,25 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
     {
       // |k| / (|u| + 1) > num / den  <=>  |k| * den > num * (|u| + 1)   (both denominators >= 1)
       const S a_num = (NU == 1) ? fabs(k[0]) : sqrt(kn);
-      const S a_den = ((NU == 1) ? fabs(blk[(size_t)L::SIZE * tpb]) : sqrt(un)) + S(1);
+      const S a_den = ((NU == 1) ? fabs(u_cur[0]) : sqrt(un)) + S(1);
       if(a_num * krn_den > krn_num * a_den)
       {
         krn_num = a_num;
         krn_den = a_den;
       }
     }
+      } while(0);
+    }
+#pragma unroll
+    for(int a = 0; a < NU; a++) u_cur[a] = u_nxt[a];
   }
   k_rel_norm = krn_num / krn_den;
-  return true;
+  return ok;
 }
 
 /** procOnce() Step 2 (DDPSolver.hpp:188-231): retry the backward sweep with larger lambda until the
-    factorisation succeeds, then the small-gradient termination test. */
+    factorisation succeeds, then the small-gradient termination test.  blockDim.x is a multiple of 32;
+    each warp owns one 32-instance tile and a private two-stage TMA ring in shared memory. */
 template<class M, bool CONSTRAINED>
 __global__ void backward_kernel(const __grid_constant__ M model,
                                 const __grid_constant__ Workspace<typename M::Scalar> ws,
@@ -708,33 +781,61 @@ __global__ void backward_kernel(const __grid_constant__ M model,
                                 int iter)
 {
   using S = typename M::Scalar;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if(b >= ws.B) return;
-  if(ws.status[b] != 0) return;
-
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  S * ring = reinterpret_cast<S *>(smem_raw);
-  const int tpb = blockDim.x;
-
-  S lambda = ws.lambda[b];
-  S dlambda = ws.dlambda[b];
-  const S * us = ws.u[ws.sel[b]];
-  int n_bwd = ws.n_bwd[b];
-  S dV0, dV1, k_rel_norm;
-  bool failed = false;
-  for(;;)
+  using L = BlockLayout<M::NX, M::NU>;
+  constexpr unsigned kFull = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_warps = blockDim.x >> 5;
+  // [n_warps][2 stages][BLK][32] tiles, then 2 mbarriers per warp
+  S * ring = reinterpret_cast<S *>(smem_raw) + (size_t)warp * 2 * L::SIZE * kTile;
+  unsigned long long * bars =
+      reinterpret_cast<unsigned long long *>(smem_raw + sizeof(S) * (size_t)n_warps * 2 * L::SIZE * kTile) + 2 * warp;
+  if(lane == 0)
   {
-    n_bwd++;
-    if(backwardSweep<M, CONSTRAINED>(ws, prm, b, us, ring, tpb, lambda, dV0, dV1, k_rel_norm)) break;
-    // increase lambda (:194-204)
-    dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
-    lambda = fmax(lambda * dlambda, prm.lambda_min);
-    if(lambda > prm.lambda_max)
+    mbarInit(&bars[0], 1);
+    mbarInit(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncwarp();
+  unsigned parity = 0u;
+
+  const int bg = blockIdx.x * blockDim.x + threadIdx.x; // ws.Bp is a multiple of 128, so the tile is always in range
+  const int b = (bg < ws.B) ? bg : bg; // padded instances read valid (padding) memory and never write
+  const bool live = (bg < ws.B) && (ws.status[bg < ws.B ? bg : 0] == 0);
+
+  S lambda = live ? ws.lambda[b] : S(0);
+  S dlambda = live ? ws.dlambda[b] : S(0);
+  const S * us = ws.u[live ? ws.sel[b] : 0];
+  int n_bwd = live ? ws.n_bwd[b] : 0;
+  S dV0 = S(0), dV1 = S(0), k_rel_norm = S(0);
+  bool need = live;
+  bool failed = false;
+  while(__any_sync(kFull, need))
+  {
+    if(need) n_bwd++;
+    const bool ok =
+        backwardSweep<M, CONSTRAINED>(ws, prm, b, lane, us, ring, bars, parity, need, lambda, dV0, dV1, k_rel_norm);
+    if(need)
     {
-      failed = true;
-      break;
+      if(ok)
+      {
+        need = false;
+      }
+      else
+      {
+        // increase lambda (:194-204)
+        dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
+        lambda = fmax(lambda * dlambda, prm.lambda_min);
+        if(lambda > prm.lambda_max)
+        {
+          failed = true;
+          need = false;
+        }
+      }
     }
   }
+  if(!live) return;
   ws.n_bwd[b] = n_bwd;
   ws.lambda[b] = lambda;
   ws.dlambda[b] = dlambda;
@@ -1063,6 +1164,22 @@ struct FwdOperands
     loop (it contains warp barriers); `work` lanes roll out their own candidate, `do_store` lanes also
     write the candidate trajectory, `gcopy` groups keep the ring fed.  Same arithmetic as
     forwardRollout => same costs. */
+template<class S>
+struct FwdDest
+{
+  S * x; //!< [N+1][NX][stride]
+  S * u; //!< [N][NU][stride]
+  S * c; //!< [N+1][stride]
+  size_t stride;
+  size_t col;
+};
+
+template<class S>
+__device__ __forceinline__ FwdDest<S> candidateBuffer(const Workspace<S> & ws, int sel, int b)
+{
+  return FwdDest<S>{ws.x[sel ^ 1], ws.u[sel ^ 1], ws.cost[sel ^ 1], (size_t)ws.Bp, (size_t)b};
+}
+
 template<class M, int GA, int DEPTH>
 __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model,
                                                                  const Workspace<typename M::Scalar> & ws,
@@ -1075,7 +1192,8 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
                                                                  typename M::Scalar alpha,
                                                                  bool work,
                                                                  bool do_store,
-                                                                 bool gcopy)
+                                                                 bool gcopy,
+                                                                 const FwdDest<typename M::Scalar> & dst)
 {
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
@@ -1085,9 +1203,10 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
   const int N = prm.N;
   const S * __restrict__ xc = ws.x[sel];
   const S * __restrict__ uc = ws.u[sel];
-  S * __restrict__ xn = ws.x[sel ^ 1];
-  S * __restrict__ un = ws.u[sel ^ 1];
-  S * __restrict__ cn = ws.cost[sel ^ 1];
+  S * __restrict__ xn = dst.x;
+  S * __restrict__ un = dst.u;
+  S * __restrict__ cn = dst.c;
+  const size_t Bd = dst.stride, bd = dst.col;
 
   // lane a of the group copies operands a, a+GA, ... of step `step` into ring slot `slot`
   auto issue = [&](int step, int slot) {
@@ -1108,11 +1227,11 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
             src = ws.kff + ((size_t)step * NU + (e - O::KFF)) * Bp + b;
           else
             src = ws.kfb + ((size_t)step * NU * NX + (e - O::KFB)) * Bp + b;
-          S * dst = ring + ((size_t)slot * O::SIZE + e) * IPW + g;
+          S * rdst = ring + ((size_t)slot * O::SIZE + e) * IPW + g;
           if constexpr(sizeof(S) == 8)
-            cpAsync8(dst, src);
+            cpAsync8(rdst, src);
           else
-            cpAsync4(dst, src);
+            cpAsync4(rdst, src);
         }
       }
     }
@@ -1125,7 +1244,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
   if(do_store)
   {
 #pragma unroll
-    for(int d = 0; d < NX; d++) xn[(size_t)d * Bp + b] = x[d];
+    for(int d = 0; d < NX; d++) xn[(size_t)d * Bd + bd] = x[d];
   }
 
   __syncwarp(); // previous users of the ring are done
@@ -1162,7 +1281,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
 #pragma unroll
         for(int j = 0; j < NX; j++) s += Kr[c + j * NU] * (x[j] - xr[j]);
         u[c] = (ur[c] + alpha * kr[c]) + s;
-        if(do_store) un[((size_t)i * NU + c) * Bp + b] = u[c];
+        if(do_store) un[((size_t)i * NU + c) * Bd + bd] = u[c];
       }
       const S t = prm.t0 + i * model.dt();
       const S c = model.runningCost(t, x, u);
@@ -1170,8 +1289,8 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
       if(do_store)
       {
 #pragma unroll
-        for(int d = 0; d < NX; d++) xn[((size_t)(i + 1) * NX + d) * Bp + b] = x[d];
-        cn[(size_t)i * Bp + b] = c;
+        for(int d = 0; d < NX; d++) xn[((size_t)(i + 1) * NX + d) * Bd + bd] = x[d];
+        cn[(size_t)i * Bd + bd] = c;
       }
       csum += c;
     }
@@ -1181,7 +1300,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
   {
     const S t = prm.t0 + N * model.dt();
     const S c = model.terminalCost(t, x);
-    if(do_store) cn[(size_t)N * Bp + b] = c;
+    if(do_store) cn[(size_t)N * Bd + bd] = c;
     csum += c;
   }
   return csum;
@@ -1235,7 +1354,7 @@ __global__ void forward_spec_kernel(const __grid_constant__ M model,
     const bool gcopy = ((work_ballot >> (g * GA)) & kGroupMask) != 0;
     const S my_alpha = prm.alpha_list[(ai < prm.n_alpha) ? ai : 0];
     const S my_cost = forwardRolloutRing<M, GA, DEPTH>(model, ws, prm, ring, g, a, b, sel, my_alpha, work,
-                                                       work && (ai == 0), gcopy);
+                                                       work && (ai == 0), gcopy, candidateBuffer<S>(ws, sel, b));
     S my_actual = S(0), my_expected = S(0), my_ratio = S(0);
     bool ok = false;
     if(work) ok = lineSearchTest<S>(prm, cost_cur, my_cost, my_alpha, dV0, dV1, my_actual, my_expected, my_ratio);
@@ -1272,7 +1391,7 @@ __global__ void forward_spec_kernel(const __grid_constant__ M model,
   if(need_ballot != 0)
   {
     const S c2 = forwardRolloutRing<M, GA, DEPTH>(model, ws, prm, ring, g, a, b, sel, alpha, need && a == 0,
-                                                  need && a == 0, need);
+                                                  need && a == 0, need, candidateBuffer<S>(ws, sel, b));
     if(need && a == 0) cost_new = c2; // bit-identical to the store-free rollout of the same candidate
   }
 
