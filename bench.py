@@ -348,8 +348,7 @@ def main():
             except Exception:
                 traffic = None
         kernel_names = {"derivative": "ddp::linearize_kernel", "backward": "ddp::backward_kernel",
-                        "forward": "ddp::forward_first_kernel + forward_fanout_kernel + forward_commit_kernel "
-                                   "(one line search = 3 launches)"}
+                        "forward": "ddp::forward_first_kernel + ddp::forward_fanout_kernel (one line search = 2 launches)"}
         roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": kernels[dominant]["achieved_gbs"],
                     "peak": peak, "unit": "GB/s", "frac": kernels[dominant]["frac"], "traffic": traffic,
                     "peak_source": peak_src, "kernels": kernels,
@@ -374,8 +373,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "timing": "host wall clock around K public-API calls with pinned host buffers"},
-            # per step: 2 layout + 1 rollout + 10 x (derivative, backward, 3 line-search phases) + 1 first-control extract
-            "gpu_launches": int(args.steps * (2 + 1 + 5 * MAX_ITER + 1)),
+            # per step: 2 layout + 1 rollout + 10 x (derivative, backward, 2 line-search phases) + 1 first-control extract
+            "gpu_launches": int(args.steps * (2 + 1 + 4 * MAX_ITER + 1)),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "work": {"iterations_mean": float(iters.mean()), "forward_passes_mean": float(n_fwd.mean()),

@@ -486,10 +486,6 @@ protected:
       const int grid = (B + kWarps * ipw - 1) / (kWarps * ipw); // worst case: every instance listed
       forward_fanout_kernel<M><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, fan_, iter);
     }
-    {
-      const dim3 block(32, 16), grid((B + 31) / 32, 8);
-      forward_commit_kernel<M><<<grid, block, 0, st>>>(ws_, prm_, fan_);
-    }
   }
 
   void ensureFanout()

@@ -14,8 +14,8 @@
  *                                    to scratch.  First success in list order wins -- identical to the
  *                                    reference's sequential backtracking because forwardPass(alpha) is a
  *                                    pure function of alpha.
- *   phase 3  forward_commit_kernel   the winners' scratch trajectories are copied into the (new) current
- *                                    buffer.
+ *   phase 3  (fused into phase 2)    each winner's scratch trajectory is copied into the (new) current buffer
+ *                                    by the 16 lanes of its group.
  *
  * A late M-fixed iteration therefore costs two rollout latencies instead of up to eleven.
  */
@@ -178,41 +178,57 @@ __global__ void forward_fanout_kernel(const __grid_constant__ M model,
   const S r_ratio = __shfl_sync(kFull, my_ratio, src);
   const S r_cost = __shfl_sync(kFull, my_cost, src);
   const S r_alpha = __shfl_sync(kFull, my_alpha, src);
-  if(!valid || a != 0) return;
-  const bool success = gm != 0;
-  fan.commit_item[slot] = success ? (int)((size_t)slot * GA + pick) : -1;
-  lineSearchFinish<S>(ws, prm, b, iter, sel, success, r_alpha, r_actual, r_expected, r_ratio, cost_cur, r_cost,
-                      success ? (2 + pick) : prm.n_alpha);
-}
-
-/** Phase 3: copy each winner's scratch trajectory into its instance's new current buffer. */
-template<class M>
-__global__ void forward_commit_kernel(const __grid_constant__ Workspace<typename M::Scalar> ws,
-                                      const __grid_constant__ SolverParams<typename M::Scalar> prm,
-                                      const __grid_constant__ FwdFanout<typename M::Scalar> fan)
-{
-  using S = typename M::Scalar;
-  constexpr int NX = M::NX, NU = M::NU;
-  const int count = *fan.count;
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if(blockIdx.x * blockDim.x >= count) return;
-  if(slot >= count) return;
-  const int item = fan.commit_item[slot];
-  if(item < 0) return;
-  const int b = fan.list[slot];
-  const int sel = ws.sel[b]; // already flipped by lineSearchFinish: the accepted trajectory lives here
-  const size_t Bp = ws.Bp;
-  const int N = prm.N;
-  const int rows_x = (N + 1) * NX, rows_u = N * NU, rows_c = N + 1;
-  for(int r = threadIdx.y + blockIdx.y * blockDim.y; r < rows_x + rows_u + rows_c; r += blockDim.y * gridDim.y)
+  const bool success = valid && (gm != 0);
+  if(valid && a == 0)
   {
-    if(r < rows_x)
-      ws.x[sel][(size_t)r * Bp + b] = fan.sx[(size_t)r * fan.items + item];
-    else if(r < rows_x + rows_u)
-      ws.u[sel][(size_t)(r - rows_x) * Bp + b] = fan.su[(size_t)(r - rows_x) * fan.items + item];
-    else
-      ws.cost[sel][(size_t)(r - rows_x - rows_u) * Bp + b] = fan.sc[(size_t)(r - rows_x - rows_u) * fan.items + item];
+    fan.commit_item[slot] = success ? (int)((size_t)slot * GA + pick) : -1;
+    lineSearchFinish<S>(ws, prm, b, iter, sel, success, r_alpha, r_actual, r_expected, r_ratio, cost_cur, r_cost,
+                        success ? (2 + pick) : prm.n_alpha);
+  }
+  // Phase 3, fused: the group copies its winner's scratch trajectory into the instance's other buffer (which
+  // lineSearchFinish has just made the current one).  The winner lane's global stores are ordered before the
+  // group's loads by the warp barrier.
+  __syncwarp();
+  if(success)
+  {
+    constexpr int NX = M::NX, NU = M::NU;
+    const int N = prm.N;
+    const size_t Bp = ws.Bp;
+    const size_t win = (size_t)slot * GA + pick;
+    const int rows_x = (N + 1) * NX, rows_u = N * NU, rows_c = N + 1;
+    S * __restrict__ dx = ws.x[sel ^ 1];
+    S * __restrict__ du = ws.u[sel ^ 1];
+    S * __restrict__ dc = ws.cost[sel ^ 1];
+    // one flat row index over (x | u | cost); 8 independent loads in flight per lane
+    const int rows = rows_x + rows_u + rows_c;
+    auto src = [&](int r) -> const S * {
+      return (r < rows_x) ? fan.sx + (size_t)r * fan.items + win
+                          : (r < rows_x + rows_u) ? fan.su + (size_t)(r - rows_x) * fan.items + win
+                                                  : fan.sc + (size_t)(r - rows_x - rows_u) * fan.items + win;
+    };
+    auto dstp = [&](int r) -> S * {
+      return (r < rows_x) ? dx + (size_t)r * Bp + b
+                          : (r < rows_x + rows_u) ? du + (size_t)(r - rows_x) * Bp + b
+                                                  : dc + (size_t)(r - rows_x - rows_u) * Bp + b;
+    };
+    for(int r0 = a; r0 < rows; r0 += GA * 8)
+    {
+      S v[8];
+#pragma unroll
+      for(int q = 0; q < 8; q++)
+      {
+        const int r = r0 + q * GA;
+        if(r < rows) v[q] = *src(r);
+      }
+#pragma unroll
+      for(int q = 0; q < 8; q++)
+      {
+        const int r = r0 + q * GA;
+        if(r < rows) *dstp(r) = v[q];
+      }
+    }
   }
 }
+
 } // namespace ddp
 } // namespace nmpc_b200
