@@ -469,6 +469,7 @@ __global__ void backward_coop_kernel(const __grid_constant__ M model,
                                      const __grid_constant__ SolverParams<typename M::Scalar> prm,
                                      int iter)
 {
+  pdlPrologue();
   using S = typename M::Scalar;
   using C = CoopLayout<M, GS>;
   constexpr unsigned kFull = 0xffffffffu;

@@ -44,6 +44,30 @@ __global__ void extract_u0_kernel(const S * u0buf, const S * u1buf, const int * 
   for(int d = 0; d < NU; d++) dst[(size_t)b * NU + d] = double(u[(size_t)d * Bp + b]);
 }
 
+/** Kernel launch, optionally with the programmatic-stream-serialization attribute (see pdlPrologue()).
+    Measured on B200 (cart-pole, B=4096, M-fixed): letting the ~45 dependent kernels of a solve pre-launch made
+    the step SLOWER (2.87 ms vs 2.18 ms) -- the early-resident grids of the wide linearisation kernel get in the
+    way of the latency-bound sweeps -- so the attribute is off unless NMPC_B200_PDL=1. */
+template<class... KArgs, class... Args>
+inline void launchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&... args)
+{
+  static const bool use_pdl = [] {
+    const char * env = std::getenv("NMPC_B200_PDL");
+    return env != nullptr && env[0] == '1';
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NMPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 template<class M>
 class DdpEngine : public DdpEngineBase
 {
@@ -163,7 +187,7 @@ public:
 
     const int tpb = threadsPerBlock(B);
     const int grid = (B + tpb - 1) / tpb;
-    rollout_init_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_);
+    launchPdl(rollout_init_kernel<M>, dim3(grid), dim3(tpb), 0, st, model_, ws_, prm_);
     launches_[0]++;
     record(st); // 2: setup done
 
@@ -173,7 +197,7 @@ public:
     iters_launched_ = 0;
     for(int iter = 1; iter <= cfg_.max_iter; iter++)
     {
-      linearize_kernel<M><<<grid1, tpb1, 0, st>>>(model_, ws_, prm_);
+      launchPdl(linearize_kernel<M>, grid1, dim3(tpb1), 0, st, model_, ws_, prm_);
       record(st);
       launchBackward(B, tpb, grid, iter, st);
       record(st);
@@ -427,7 +451,7 @@ protected:
                            (int)smem);
       attr_set = true;
     }
-    backward_coop_kernel<M, kCoopGS, CONSTRAINED><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, iter);
+    launchPdl(backward_coop_kernel<M, kCoopGS, CONSTRAINED>, dim3(grid), dim3(kWarps * 32), smem, st, model_, ws_, prm_, iter);
   }
 
   void launchBackward(int B, int tpb, int grid, int iter, cudaStream_t st)
@@ -441,9 +465,9 @@ protected:
       return;
     }
     if(cfg_.with_input_constraint)
-      backward_kernel<M, true><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
+      launchPdl(backward_kernel<M, true>, dim3(grid), dim3(tpb), backwardSmemBytes(tpb), st, model_, ws_, prm_, iter);
     else
-      backward_kernel<M, false><<<grid, tpb, backwardSmemBytes(tpb), st>>>(model_, ws_, prm_, iter);
+      launchPdl(backward_kernel<M, false>, dim3(grid), dim3(tpb), backwardSmemBytes(tpb), st, model_, ws_, prm_, iter);
   }
 
   template<int GA>
@@ -459,7 +483,7 @@ protected:
       cudaFuncSetAttribute(forward_spec_kernel<M, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       attr_set = true;
     }
-    forward_spec_kernel<M, GA><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, iter);
+    launchPdl(forward_spec_kernel<M, GA>, dim3(grid), dim3(kWarps * 32), smem, st, model_, ws_, prm_, iter);
   }
 
   /** Three-phase line search (ddp_forward_phased.cuh). */
@@ -476,15 +500,15 @@ protected:
         cudaFuncSetAttribute(forward_first_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
       }
-      forward_first_kernel<M><<<(B + kWarps * 32 - 1) / (kWarps * 32), kWarps * 32, smem, st>>>(model_, ws_, prm_, fan_,
-                                                                                             iter);
+      launchPdl(forward_first_kernel<M>, dim3((B + kWarps * 32 - 1) / (kWarps * 32)), dim3(kWarps * 32), smem, st, model_,
+                ws_, prm_, fan_, iter);
     }
     {
       constexpr int kWarps = 4;
       constexpr int ipw = 32 / kFanLanes;
       const size_t smem = sizeof(S) * (size_t)kWarps * 4 * O::SIZE * ipw;
       const int grid = (B + kWarps * ipw - 1) / (kWarps * ipw); // worst case: every instance listed
-      forward_fanout_kernel<M><<<grid, kWarps * 32, smem, st>>>(model_, ws_, prm_, fan_, iter);
+      launchPdl(forward_fanout_kernel<M>, dim3(grid), dim3(kWarps * 32), smem, st, model_, ws_, prm_, fan_, iter);
     }
   }
 
@@ -518,7 +542,7 @@ protected:
         launchForwardPhased(B, iter, st);
         break;
       default:
-        forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+        launchPdl(forward_kernel<M>, dim3(grid), dim3(tpb), 0, st, model_, ws_, prm_, iter);
     }
   }
 

@@ -96,6 +96,7 @@ __global__ void forward_first_kernel(const __grid_constant__ M model,
                                      const __grid_constant__ FwdFanout<typename M::Scalar> fan,
                                      int iter)
 {
+  pdlPrologue();
   using S = typename M::Scalar;
   constexpr int DEPTH = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,6 +137,7 @@ __global__ void forward_fanout_kernel(const __grid_constant__ M model,
                                       const __grid_constant__ FwdFanout<typename M::Scalar> fan,
                                       int iter)
 {
+  pdlPrologue();
   using S = typename M::Scalar;
   constexpr int GA = kFanLanes;
   constexpr int IPW = 32 / GA;

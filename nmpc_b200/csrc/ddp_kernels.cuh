@@ -98,6 +98,17 @@ struct BlockLayout
   static constexpr int SIZE = LXU + NX * NU;
 };
 
+/** Programmatic dependent launch (sm_90+): every stage kernel starts with pdlPrologue().  It lets the NEXT
+    kernel of the stream be launched and made resident right away (launch_dependents) and then waits until the
+    PREVIOUS kernel has completed and flushed its results (griddepcontrol.wait), so the launch latency between
+    the ~45 dependent kernels of one solve overlaps with the tail of the predecessor.  Without the launch
+    attribute both instructions are no-ops. */
+__device__ __forceinline__ void pdlPrologue()
+{
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
 template<class S>
 __device__ __forceinline__ S ldStream(const S * p)
 {
@@ -217,6 +228,7 @@ __global__ void rollout_init_kernel(const __grid_constant__ M model,
                                     const __grid_constant__ Workspace<typename M::Scalar> ws,
                                     const __grid_constant__ SolverParams<typename M::Scalar> prm)
 {
+  pdlPrologue();
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,6 +281,7 @@ __global__ void linearize_kernel(const __grid_constant__ M model,
                                  const __grid_constant__ Workspace<typename M::Scalar> ws,
                                  const __grid_constant__ SolverParams<typename M::Scalar> prm)
 {
+  pdlPrologue();
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
   using L = BlockLayout<NX, NU>;
@@ -780,6 +793,7 @@ __global__ void backward_kernel(const __grid_constant__ M model,
                                 const __grid_constant__ SolverParams<typename M::Scalar> prm,
                                 int iter)
 {
+  pdlPrologue();
   using S = typename M::Scalar;
   using L = BlockLayout<M::NX, M::NU>;
   constexpr unsigned kFull = 0xffffffffu;
@@ -994,6 +1008,7 @@ __global__ void forward_kernel(const __grid_constant__ M model,
                                const __grid_constant__ SolverParams<typename M::Scalar> prm,
                                int iter)
 {
+  pdlPrologue();
   using S = typename M::Scalar;
   constexpr unsigned kFull = 0xffffffffu;
   const int bg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1318,6 +1333,7 @@ __global__ void forward_spec_kernel(const __grid_constant__ M model,
                                     const __grid_constant__ SolverParams<typename M::Scalar> prm,
                                     int iter)
 {
+  pdlPrologue();
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
   constexpr int IPW = 32 / GA;
