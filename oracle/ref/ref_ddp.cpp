@@ -10,6 +10,10 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <vector>
+#ifdef _OPENMP
+#  include <omp.h>
+#endif
 
 #include <nmpc_ddp/BoxQP.h>
 #include <nmpc_ddp/DDPSolver.h>
@@ -135,6 +139,77 @@ int ref_ddp_solve_cartpole(const double * params,
   }
   *n_trace_out = (int)tl.size();
   return 0;
+}
+
+/** A batch of cart-pole solves with the reference's code: one DDPSolver object per OpenMP thread, instances
+    handed out dynamically ("N independent DDPSolver instances").  Outputs: first-step control, total cost,
+    iteration count per instance.  The timed CPU arm of bench.py (informational: the Eigen stand-in is
+    heap-backed, so this under-states what the reference achieves with real Eigen). */
+int ref_ddp_solve_cartpole_batch(const double * params,
+                                 const ref_ddp_config * cfg,
+                                 int B,
+                                 double t0,
+                                 const double * x0,
+                                 const double * u_init,
+                                 int nthreads,
+                                 double * u0_out,
+                                 double * cost_out,
+                                 int * iters_out)
+{
+  const int N = cfg->horizon_steps;
+  int err = 0;
+  std::streambuf * old = std::cout.rdbuf(nullptr);
+#ifdef _OPENMP
+  if(nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+  {
+    auto problem = std::make_shared<DDPProblemCartPole>(params);
+    nmpc_ddp::DDPSolver<4, 1> solver(problem);
+    auto & c = solver.config();
+    c.print_level = 0;
+    c.with_input_constraint = false;
+    c.max_iter = cfg->max_iter;
+    c.horizon_steps = N;
+    c.reg_type = cfg->reg_type;
+    c.initial_lambda = cfg->initial_lambda;
+    c.initial_dlambda = cfg->initial_dlambda;
+    c.lambda_factor = cfg->lambda_factor;
+    c.lambda_min = cfg->lambda_min;
+    c.lambda_max = cfg->lambda_max;
+    c.k_rel_norm_thre = cfg->k_rel_norm_thre;
+    c.lambda_thre = cfg->lambda_thre;
+    c.alpha_list.resize(cfg->n_alpha);
+    for(int i = 0; i < cfg->n_alpha; i++) c.alpha_list[i] = cfg->alpha_list[i];
+    c.cost_update_ratio_thre = cfg->cost_update_ratio_thre;
+    c.cost_update_thre = cfg->cost_update_thre;
+    std::vector<DDPProblemCartPole::InputDimVector> initial_u_list(N);
+#pragma omp for schedule(dynamic, 4)
+    for(int b = 0; b < B; b++)
+    {
+      DDPProblemCartPole::StateDimVector current_x;
+      current_x << x0[4 * b + 0], x0[4 * b + 1], x0[4 * b + 2], x0[4 * b + 3];
+      for(int i = 0; i < N; i++) initial_u_list[i][0] = u_init[(size_t)b * N + i];
+      try
+      {
+        solver.solve(t0, current_x, initial_u_list);
+      }
+      catch(...)
+      {
+#pragma omp atomic write
+        err = -1;
+        continue;
+      }
+      const auto & cd = solver.controlData();
+      if(u0_out) u0_out[b] = cd.u_list[0][0];
+      if(cost_out) cost_out[b] = cd.cost_list.sum();
+      if(iters_out) iters_out[b] = solver.traceDataList().back().iter;
+    }
+  }
+  std::cout.rdbuf(old);
+  return err;
 }
 
 /** nmpc_ddp::BoxQP<2>::solve / BoxQP<Dynamic>::solve with the reference's code (TestBoxQP.cpp cases). */
