@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "ddp_kernels.cuh"
 #include "ddp_backward_coop.cuh"
+#include "ddp_backward_quad.cuh"
 #include "ddp_forward_phased.cuh"
 #include "registry.h"
 
@@ -396,6 +397,7 @@ public:
 protected:
   static constexpr int kMaxThreadsPerBlock = 128;
   static constexpr bool kHasBoxQP = true;
+  static constexpr size_t kQuadSmemLimit = 200 * 1024; //!< shared memory the column-split K2 may use per CTA
   static constexpr int kPhased = 3; //!< K3 variant id: three-phase line search
   // group size of the cooperative K2: the power of two >= NX, capped at a warp
   static constexpr int kCoopGS = (NX <= 1) ? 1 : (NX <= 2) ? 2 : (NX <= 4) ? 4 : (NX <= 8) ? 8 : (NX <= 16) ? 16 : 32;
@@ -454,8 +456,50 @@ protected:
     launchPdl(backward_coop_kernel<M, kCoopGS, CONSTRAINED>, dim3(grid), dim3(kWarps * 32), smem, st, model_, ws_, prm_, iter);
   }
 
+  /** K2 variant for latency-bound batches: four warps per 32-instance tile (ddp_backward_quad.cuh). */
+  static bool backwardUsesQuad(int B)
+  {
+    if(QuadLayout<M>::bytes() > kQuadSmemLimit) return false;
+    if(const char * env = std::getenv("NMPC_B200_BWD_QUAD"))
+    {
+      if(env[0] == '0') return false;
+      if(env[0] == '1') return true;
+    }
+    // Measured on B200: for n_x = 4 (cart-pole, B=4096) the three barriers per step cost what the split saves
+    // (107 us vs 84 us per sweep; both variants are bound by one warp's dependent chain); for n_x = 12 (quadrotor
+    // fp32, B=8192) the split beats both alternatives (14.5 ms vs 20.8 ms per 10 sweeps for the in-warp variant).
+    if(NX < 8) return false;
+    return B <= 148 * 4 * 32;
+  }
+
+  template<bool CONSTRAINED>
+  void launchBackwardQuad(int B, int iter, cudaStream_t st)
+  {
+    const size_t smem = QuadLayout<M>::bytes();
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_quad_kernel<M, CONSTRAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+      attr_set = true;
+    }
+    launchPdl(backward_quad_kernel<M, CONSTRAINED>, dim3((B + kTile - 1) / kTile), dim3(kQuadWarps * 32), smem, st, model_,
+              ws_, prm_, iter);
+  }
+
   void launchBackward(int B, int tpb, int grid, int iter, cudaStream_t st)
   {
+    if constexpr(QuadLayout<M>::bytes() <= kQuadSmemLimit)
+    {
+      if(backwardUsesQuad(B))
+      {
+        if(cfg_.with_input_constraint)
+          launchBackwardQuad<true>(B, iter, st);
+        else
+          launchBackwardQuad<false>(B, iter, st);
+        return;
+      }
+    }
     if(backwardLanesPerInstance(B) > 1)
     {
       if(cfg_.with_input_constraint)

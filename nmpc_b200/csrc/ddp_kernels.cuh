@@ -448,9 +448,13 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
   S k_prev[NU]; // k_list_[i + 1], the BoxQP warm start (:452-467)
 #pragma unroll
   for(int a = 0; a < NU; a++) k_prev[a] = S(0);
-  S u_cur[NU], u_nxt[NU]; // u_i for the termination test / input limits, fetched one step ahead
+  S u_cur[NU], u_nxt[NU], u_nx2[NU]; // u_i for the termination test / input limits, fetched two steps ahead
 #pragma unroll
-  for(int a = 0; a < NU; a++) u_cur[a] = us[((size_t)(N - 1) * NU + a) * Bp + b];
+  for(int a = 0; a < NU; a++)
+  {
+    u_cur[a] = us[((size_t)(N - 1) * NU + a) * Bp + b];
+    u_nxt[a] = us[((size_t)(N > 1 ? N - 2 : 0) * NU + a) * Bp + b];
+  }
   bool ok = true;
 
   for(int i = N - 1; i >= 0; i--)
@@ -459,9 +463,9 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
     __syncwarp(); // every lane has finished reading the other stage (step i+1)
     if(i > 0) stageStep(stage ^ 1, i - 1);
     {
-      const int ip = (i > 0) ? i - 1 : 0;
+      const int ip = (i > 1) ? i - 2 : 0;
 #pragma unroll
-      for(int a = 0; a < NU; a++) u_nxt[a] = us[((size_t)ip * NU + a) * Bp + b];
+      for(int a = 0; a < NU; a++) u_nx2[a] = us[((size_t)ip * NU + a) * Bp + b];
     }
     mbarWait(&bars[stage], (parity >> stage) & 1u);
     parity ^= (1u << stage);
@@ -778,7 +782,11 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
       } while(0);
     }
 #pragma unroll
-    for(int a = 0; a < NU; a++) u_cur[a] = u_nxt[a];
+    for(int a = 0; a < NU; a++)
+    {
+      u_cur[a] = u_nxt[a];
+      u_nxt[a] = u_nx2[a];
+    }
   }
   k_rel_norm = krn_num / krn_den;
   return ok;

@@ -47,6 +47,46 @@ __global__ void op_kernel(double * out, long long * cyc, double a, int iters)
   if(threadIdx.x == 0) *cyc = t1 - t0;
 }
 
+
+// DFMA issue rate of ONE warp with only `active` lanes enabled (does the fp64 pipe skip an idle half-warp?)
+__global__ void dfma_partial_kernel(double * out, long long * cyc, double a, double b, int iters, int active)
+{
+  if((int)threadIdx.x >= active) return;
+  double v[16];
+  for(int c = 0; c < 16; c++) v[c] = threadIdx.x * 1e-3 + c;
+  long long t0 = clock64();
+  for(int i = 0; i < iters; i++)
+  {
+#pragma unroll
+    for(int c = 0; c < 16; c++) v[c] = fma(v[c], a, b);
+  }
+  long long t1 = clock64();
+  double s = 0;
+  for(int c = 0; c < 16; c++) s += v[c];
+  out[threadIdx.x] = s;
+  if(threadIdx.x == 0) *cyc = t1 - t0;
+}
+
+// Round trip of one value through shared memory between the 4 warps of a CTA: STS, bar.sync, LDS of the
+// neighbour warp's value, one dependent DFMA (the exchange step of a column-split Riccati sweep).
+__global__ void exchange_kernel(double * out, long long * cyc, double a, int iters)
+{
+  __shared__ double buf[4][32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double v = 0.3 + threadIdx.x * 1e-3;
+  long long t0 = clock64();
+  for(int i = 0; i < iters; i++)
+  {
+    buf[w][l] = v;
+    __syncthreads();
+    v = fma(buf[(w + 1) & 3][l], a, 0.25);
+    __syncthreads();
+  }
+  long long t1 = clock64();
+  out[threadIdx.x] = v;
+  if(threadIdx.x == 0) *cyc = t1 - t0;
+}
+
 int main()
 {
   double * out;
@@ -88,5 +128,18 @@ int main()
     printf("DFMA 8 chains x %d warps: %.2f cyc/iter (warp 0) => %.2f warp-DFMA/cyc/SM\n", w, double(*cyc) / iters,
            8.0 * w / (double(*cyc) / iters));
   }
+  for(int act : {32, 16, 8, 4})
+  {
+    dfma_partial_kernel<<<1, 32>>>(out, cyc, 0.999, 1e-3, iters, act);
+    cudaDeviceSynchronize();
+    dfma_partial_kernel<<<1, 32>>>(out, cyc, 0.999, 1e-3, iters, act);
+    cudaDeviceSynchronize();
+    printf("DFMA 16 chains, %2d active lanes: %.2f cyc/DFMA\n", act, double(*cyc) / iters / 16);
+  }
+  exchange_kernel<<<1, 128>>>(out, cyc, 0.999, iters);
+  cudaDeviceSynchronize();
+  exchange_kernel<<<1, 128>>>(out, cyc, 0.999, iters);
+  cudaDeviceSynchronize();
+  printf("smem exchange (STS, bar.sync, LDS, DFMA, bar.sync) x 4 warps: %.1f cyc/round\n", double(*cyc) / iters);
   return 0;
 }
