@@ -183,6 +183,50 @@ extern "C"
   int nmpc_b200_ddp_enable_timing(nmpc_b200_ddp * h, int enable);
   int nmpc_b200_ddp_get_durations(nmpc_b200_ddp * h, double * ms, int * launches);
 
+  /* ------------------------------------------------------- receding-horizon (MPC) loop ---- */
+
+  /** The MPC loops that call the solvers in the reference (TestDDPBipedal.cpp:243-268,
+      TestDDPCartPole.cpp:313-343 + :388-396, TestFmpcOscillator.cpp:166-190), run for a whole batch ON THE DEVICE:
+      tick after tick { solve; apply u_list[0] to the plant; warm-start the next solve } with no host round trip.
+        plant = 0   current_x <- controlData().x_list[1]                      (TestDDPBipedal.cpp:264)
+        plant = 1   current_x <- stateEq(t, current_x, u, sim_dt), n_substeps times per tick, u held
+                    (TestDDPCartPole.cpp:330, TestFmpcOscillator.cpp:187); needs a functor with the 4-argument
+                    stateEq overload, else NMPC_B200_ERR_UNSUPPORTED
+        shift_inputs = 1   initial_u_list <- u_list[1:], last entry repeated  (TestDDPBipedal.cpp:265-267)
+        shift_inputs = 0   initial_u_list <- u_list                           (TestDDPCartPole.cpp:395)
+        clamp_u0 = 1       the applied input is u_list[0] clamped to the input limits (TestDDPCartPole.cpp:393-394;
+                           needs nmpc_b200_ddp_set_input_limits)
+      current_t advances by tick_dt per tick. */
+  typedef struct
+  {
+    int n_ticks;
+    int plant;
+    int shift_inputs;
+    int clamp_u0;
+    int n_substeps;
+    int reserved;
+    double tick_dt;
+    double sim_dt;
+  } nmpc_b200_mpc_config;
+
+  /** Run n_ticks of the loop from (current_t, x0[B][NX], u_init[B][N][NU]).  Logs (any may be NULL; host or device
+      according to `on_device`): x_log[B][n_ticks+1][NX] = current_x at every tick and after the last one,
+      u_log[B][n_ticks][NU] = the applied input, iters_log[B][n_ticks] = traceDataList().back().iter,
+      status_log[B][n_ticks] = last procOnce retval.  Afterwards the handle holds the LAST solve (nmpc_b200_ddp_get). */
+  int nmpc_b200_ddp_run_mpc(nmpc_b200_ddp * h,
+                            int B,
+                            double current_t,
+                            const double * x0,
+                            const double * u_init,
+                            int n_u_steps,
+                            const nmpc_b200_mpc_config * mpc,
+                            double * x_log,
+                            double * u_log,
+                            int * iters_log,
+                            int * status_log,
+                            int on_device,
+                            void * stream);
+
   /* ---------------------------------------------------------------------------- FMPC ---- */
 
   /** Mirror of FmpcSolver::Configuration (FmpcSolver.h:58-89). */

@@ -51,6 +51,20 @@ class DdpConfigStruct(C.Structure):
     ]
 
 
+class MpcConfigStruct(C.Structure):
+    """nmpc_b200_mpc_config (c_api.h): the reference's host MPC loops, run on the device."""
+    _fields_ = [
+        ("n_ticks", C.c_int),
+        ("plant", C.c_int),
+        ("shift_inputs", C.c_int),
+        ("clamp_u0", C.c_int),
+        ("n_substeps", C.c_int),
+        ("reserved", C.c_int),
+        ("tick_dt", C.c_double),
+        ("sim_dt", C.c_double),
+    ]
+
+
 class FmpcConfigStruct(C.Structure):
     _fields_ = [
         ("horizon_steps", C.c_int),
@@ -72,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "nmpc_b200_model_default_params", "nmpc_b200_model_count", "nmpc_b200_model_name", "nmpc_b200_model_eval",
     "nmpc_b200_ddp_config_default", "nmpc_b200_ddp_create", "nmpc_b200_ddp_destroy", "nmpc_b200_ddp_set_config",
     "nmpc_b200_ddp_get_config", "nmpc_b200_ddp_set_input_limits", "nmpc_b200_ddp_solve", "nmpc_b200_ddp_get",
-    "nmpc_b200_ddp_sync", "nmpc_b200_ddp_enable_timing", "nmpc_b200_ddp_get_durations",
+    "nmpc_b200_ddp_sync", "nmpc_b200_ddp_enable_timing", "nmpc_b200_ddp_get_durations", "nmpc_b200_ddp_run_mpc",
     "nmpc_b200_fmpc_config_default", "nmpc_b200_fmpc_create", "nmpc_b200_fmpc_destroy", "nmpc_b200_fmpc_set_config",
     "nmpc_b200_fmpc_solve", "nmpc_b200_fmpc_get", "nmpc_b200_fmpc_sync", "nmpc_b200_fmpc_enable_timing",
     "nmpc_b200_fmpc_get_durations",
@@ -101,6 +115,8 @@ def lib():
         L.nmpc_b200_ddp_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                           C.c_void_p]
         L.nmpc_b200_ddp_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.nmpc_b200_ddp_run_mpc.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.nmpc_b200_ddp_create.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.nmpc_b200_ddp_destroy.argtypes = [C.c_void_p]
         L.nmpc_b200_ddp_set_config.argtypes = [C.c_void_p, C.c_void_p]

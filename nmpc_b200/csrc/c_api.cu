@@ -300,6 +300,28 @@ int nmpc_b200_ddp_solve(nmpc_b200_ddp * h,
   });
 }
 
+int nmpc_b200_ddp_run_mpc(nmpc_b200_ddp * h,
+                          int B,
+                          double current_t,
+                          const double * x0,
+                          const double * u_init,
+                          int n_u_steps,
+                          const nmpc_b200_mpc_config * mpc,
+                          double * x_log,
+                          double * u_log,
+                          int * iters_log,
+                          int * status_log,
+                          int on_device,
+                          void * stream)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_HANDLE(h);
+    if(mpc == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null mpc configuration");
+    h->engine->runMpc(B, current_t, x0, u_init, n_u_steps, *mpc, x_log, u_log, iters_log, status_log, on_device != 0,
+                      stream);
+  });
+}
+
 int nmpc_b200_ddp_get(nmpc_b200_ddp * h, int what, void * dst, size_t dst_bytes, int dst_on_device, void * stream)
 {
   return guarded([&] {

@@ -52,6 +52,11 @@ struct DeviceBuffer
     NMPC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T)));
     count = n;
   }
+  /** Grow-only variant of allocate(): keeps the buffer when it is already large enough. */
+  void reserve(size_t n)
+  {
+    if(count < n) allocate(n);
+  }
   void release()
   {
     if(ptr) cudaFree(ptr);

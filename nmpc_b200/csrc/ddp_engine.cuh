@@ -20,6 +20,7 @@
 #include "ddp_backward_coop.cuh"
 #include "ddp_backward_quad.cuh"
 #include "ddp_forward_phased.cuh"
+#include "ddp_mpc.cuh"
 #include "registry.h"
 
 namespace nmpc_b200
@@ -135,89 +136,96 @@ public:
       override
   {
     DeviceGuard guard(device_);
-    const int N = cfg_.horizon_steps;
-    // DDPSolver.hpp:41-45
-    if(n_u_steps != N)
-    {
-      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "initial_u_list length should be " + std::to_string(N) + " but "
-                                                      + std::to_string(n_u_steps) + ".");
-    }
-    if(B <= 0 || B > capacity_)
-    {
-      throw Error(NMPC_B200_ERR_CAPACITY,
-                  "batch " + std::to_string(B) + " outside (0, capacity " + std::to_string(capacity_) + "]");
-    }
-    if(x0 == nullptr || u_init == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null input array");
-    // DDPSolver.hpp:391-414: the reference throws as soon as the backward pass runs
-    if(cfg_.use_state_eq_second_derivative)
-    {
-      throw Error(NMPC_B200_ERR_RUNTIME, "Vector-tensor product is not implemented yet.");
-    }
-    if(cfg_.with_input_constraint && !have_limits_)
-    {
-      throw Error(NMPC_B200_ERR_RUNTIME, "with_input_constraint is set but no input limits were given");
-    }
-    if(cfg_.with_input_constraint && !kHasBoxQP)
-    {
-      throw Error(NMPC_B200_ERR_UNSUPPORTED,
-                  "with_input_constraint (BoxQP branch, DDPSolver.hpp:450-497) is not implemented on the device yet");
-    }
-
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : own_stream_;
-    last_stream_ = st;
-    B_ = B;
-    ws_.B = B;
-    prm_.t0 = S(current_t);
+    cudaStream_t st = beginSolve(B, n_u_steps, x0, u_init, stream);
     n_events_used_ = 0;
-    launches_[0] = launches_[1] = launches_[2] = launches_[3] = 0;
-
     record(st); // 0: start
-    const double * d_x0 = x0;
-    const double * d_u = u_init;
-    if(!on_device)
-    {
-      NMPC_CUDA_CHECK(cudaMemcpyAsync(stage_in_x_.ptr, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
-      NMPC_CUDA_CHECK(
-          cudaMemcpyAsync(stage_in_u_.ptr, u_init, sizeof(double) * (size_t)B * N * NU, cudaMemcpyHostToDevice, st));
-      d_x0 = stage_in_x_.ptr;
-      d_u = stage_in_u_.ptr;
-    }
-    record(st); // 1: inputs on device
-    launchScatterRows<double, S>(d_x0, ws_.x[0], B, NX, Bp_, st);
-    launchScatterRows<double, S>(d_u, ws_.u[0], B, N * NU, Bp_, st);
+    stageInputs(B, x0, u_init, on_device, st);
+    runIterations(B, current_t, st);
+  }
 
-    const int tpb = threadsPerBlock(B);
-    const int grid = (B + tpb - 1) / tpb;
-    launchPdl(rollout_init_kernel<M>, dim3(grid), dim3(tpb), 0, st, model_, ws_, prm_);
-    launches_[0]++;
-    record(st); // 2: setup done
+  /** The reference's MPC loops for the whole batch, tick after tick on the device (c_api.h, ddp_mpc.cuh). */
+  void runMpc(int B,
+              double current_t,
+              const double * x0,
+              const double * u_init,
+              int n_u_steps,
+              const nmpc_b200_mpc_config & mpc,
+              double * x_log,
+              double * u_log,
+              int * iters_log,
+              int * status_log,
+              bool on_device,
+              void * stream) override
+  {
+    DeviceGuard guard(device_);
+    if(mpc.n_ticks <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "n_ticks must be positive");
+    if(mpc.plant != 0 && mpc.plant != 1) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "plant must be 0 or 1");
+    if(mpc.plant == 1 && !HasStateEqDt<M>::value)
+      throw Error(NMPC_B200_ERR_UNSUPPORTED, "plant = 1 needs a functor with stateEq(t, x, u, dt)");
+    if(mpc.plant == 1 && mpc.n_substeps <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "n_substeps must be positive");
+    if(mpc.clamp_u0 && !have_limits_) throw Error(NMPC_B200_ERR_RUNTIME, "clamp_u0 is set but no input limits were given");
+    cudaStream_t st = beginSolve(B, n_u_steps, x0, u_init, stream);
+    const size_t T = mpc.n_ticks;
+    const size_t Bp = Bp_;
+    MpcLogs<S> logs{};
+    if(x_log) logs.x = (mpc_x_.reserve((T + 1) * NX * Bp), mpc_x_.ptr);
+    if(u_log) logs.u = (mpc_u_.reserve(T * NU * Bp), mpc_u_.ptr);
+    if(iters_log || status_log) mpc_i_.reserve(2 * T * Bp);
+    if(iters_log) logs.iters = mpc_i_.ptr;
+    if(status_log) logs.status = mpc_i_.ptr + T * Bp;
+    MpcParams<S> mp{};
+    mp.n_ticks = mpc.n_ticks;
+    mp.plant = mpc.plant;
+    mp.shift_inputs = mpc.shift_inputs;
+    mp.clamp_u0 = mpc.clamp_u0;
+    mp.n_substeps = mpc.n_substeps;
+    mp.tick_dt = S(mpc.tick_dt);
+    mp.sim_dt = S(mpc.sim_dt);
 
-    const int tpb1 = 128;
-    const dim3 grid1((B + tpb1 - 1) / tpb1, N + 1);
-    iter_event_base_ = n_events_used_;
-    iters_launched_ = 0;
-    for(int iter = 1; iter <= cfg_.max_iter; iter++)
+    n_events_used_ = 0;
+    record(st);
+    stageInputs(B, x0, u_init, on_device, st);
+    for(int tick = 0; tick < mpc.n_ticks; tick++)
     {
-      launchPdl(linearize_kernel<M>, grid1, dim3(tpb1), 0, st, model_, ws_, prm_);
-      record(st);
-      launchBackward(B, tpb, grid, iter, st);
-      record(st);
-      launchForward(B, tpb, grid, iter, st);
-      record(st);
-      launches_[1]++;
-      launches_[2]++;
-      launches_[3]++;
-      iters_launched_ = iter;
-      if(iter % kCheckStride == 0 && iter < cfg_.max_iter)
+      const double t = current_t + tick * mpc.tick_dt;
+      if(tick > 0)
       {
-        NMPC_CUDA_CHECK(cudaMemsetAsync(d_counter_.ptr, 0, sizeof(int), st));
-        count_active_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws_.status, B, d_counter_.ptr);
-        NMPC_CUDA_CHECK(cudaMemcpyAsync(h_counter_, d_counter_.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
-        NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
-        if(*h_counter_ == 0) break;
+        // per-tick event bookkeeping restarts so that computationDuration() describes the last solve
+        n_events_used_ = 0;
+        record(st);
+        record(st);
       }
+      runIterations(B, t, st);
+      mpc_advance_kernel<M><<<(B + 127) / 128, 128, 0, st>>>(model_, ws_, prm_, mp, logs, tick, S(t));
+      NMPC_CUDA_CHECK(cudaGetLastError());
     }
-    record(st); // end of optimisation loop
+    // logs back to instance-major
+    auto out_f64 = [&](const S * src, double * dst, int R) {
+      if(dst == nullptr) return;
+      const size_t need = sizeof(double) * (size_t)B * R;
+      double * d_out = on_device ? dst : stageOut(need);
+      launchGatherRows<S, double>(src, src, nullptr, nullptr, 0, 1, d_out, B, R, Bp_, st);
+      if(!on_device)
+      {
+        NMPC_CUDA_CHECK(cudaMemcpyAsync(dst, d_out, need, cudaMemcpyDeviceToHost, st));
+        NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+    };
+    auto out_i32 = [&](const int * src, int * dst, int R) {
+      if(dst == nullptr) return;
+      const size_t need = sizeof(int) * (size_t)B * R;
+      int * d_out = on_device ? dst : reinterpret_cast<int *>(stageOut(need));
+      launchGatherRows<int, int>(src, src, nullptr, nullptr, 0, 1, d_out, B, R, Bp_, st);
+      if(!on_device)
+      {
+        NMPC_CUDA_CHECK(cudaMemcpyAsync(dst, d_out, need, cudaMemcpyDeviceToHost, st));
+        NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+    };
+    out_f64(logs.x, x_log, (mpc.n_ticks + 1) * NX);
+    out_f64(logs.u, u_log, mpc.n_ticks * NU);
+    out_i32(logs.iters, iters_log, mpc.n_ticks);
+    out_i32(logs.status, status_log, mpc.n_ticks);
     NMPC_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -395,6 +403,98 @@ public:
   }
 
 protected:
+  /** Argument checks of DDPSolver::solve (DDPSolver.hpp:41-56, :391-414) and per-solve bookkeeping. */
+  cudaStream_t beginSolve(int B, int n_u_steps, const double * x0, const double * u_init, void * stream)
+  {
+    const int N = cfg_.horizon_steps;
+    // DDPSolver.hpp:41-45
+    if(n_u_steps != N)
+    {
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "initial_u_list length should be " + std::to_string(N) + " but "
+                                                      + std::to_string(n_u_steps) + ".");
+    }
+    if(B <= 0 || B > capacity_)
+    {
+      throw Error(NMPC_B200_ERR_CAPACITY,
+                  "batch " + std::to_string(B) + " outside (0, capacity " + std::to_string(capacity_) + "]");
+    }
+    if(x0 == nullptr || u_init == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null input array");
+    // DDPSolver.hpp:391-414: the reference throws as soon as the backward pass runs
+    if(cfg_.use_state_eq_second_derivative)
+    {
+      throw Error(NMPC_B200_ERR_RUNTIME, "Vector-tensor product is not implemented yet.");
+    }
+    if(cfg_.with_input_constraint && !have_limits_)
+    {
+      throw Error(NMPC_B200_ERR_RUNTIME, "with_input_constraint is set but no input limits were given");
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : own_stream_;
+    last_stream_ = st;
+    B_ = B;
+    ws_.B = B;
+    return st;
+  }
+
+  /** Instance-major x0 / initial_u_list (host or device) -> x_list[0] and u_list of trajectory buffer 0. */
+  void stageInputs(int B, const double * x0, const double * u_init, bool on_device, cudaStream_t st)
+  {
+    const int N = cfg_.horizon_steps;
+    const double * d_x0 = x0;
+    const double * d_u = u_init;
+    if(!on_device)
+    {
+      NMPC_CUDA_CHECK(cudaMemcpyAsync(stage_in_x_.ptr, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
+      NMPC_CUDA_CHECK(
+          cudaMemcpyAsync(stage_in_u_.ptr, u_init, sizeof(double) * (size_t)B * N * NU, cudaMemcpyHostToDevice, st));
+      d_x0 = stage_in_x_.ptr;
+      d_u = stage_in_u_.ptr;
+    }
+    record(st); // 1: inputs on device
+    launchScatterRows<double, S>(d_x0, ws_.x[0], B, NX, Bp_, st);
+    launchScatterRows<double, S>(d_u, ws_.u[0], B, N * NU, Bp_, st);
+  }
+
+  /** K0, then max_iter x {K1, K2, K3} from the inputs staged in trajectory buffer 0. */
+  void runIterations(int B, double current_t, cudaStream_t st)
+  {
+    const int N = cfg_.horizon_steps;
+    prm_.t0 = S(current_t);
+    launches_[0] = launches_[1] = launches_[2] = launches_[3] = 0;
+    const int tpb = threadsPerBlock(B);
+    const int grid = (B + tpb - 1) / tpb;
+    launchPdl(rollout_init_kernel<M>, dim3(grid), dim3(tpb), 0, st, model_, ws_, prm_);
+    launches_[0]++;
+    record(st); // 2: setup done
+
+    const int tpb1 = 128;
+    const dim3 grid1((B + tpb1 - 1) / tpb1, N + 1);
+    iter_event_base_ = n_events_used_;
+    iters_launched_ = 0;
+    for(int iter = 1; iter <= cfg_.max_iter; iter++)
+    {
+      launchPdl(linearize_kernel<M>, grid1, dim3(tpb1), 0, st, model_, ws_, prm_);
+      record(st);
+      launchBackward(B, tpb, grid, iter, st);
+      record(st);
+      launchForward(B, tpb, grid, iter, st);
+      record(st);
+      launches_[1]++;
+      launches_[2]++;
+      launches_[3]++;
+      iters_launched_ = iter;
+      if(iter % kCheckStride == 0 && iter < cfg_.max_iter)
+      {
+        NMPC_CUDA_CHECK(cudaMemsetAsync(d_counter_.ptr, 0, sizeof(int), st));
+        count_active_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws_.status, B, d_counter_.ptr);
+        NMPC_CUDA_CHECK(cudaMemcpyAsync(h_counter_, d_counter_.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+        if(*h_counter_ == 0) break;
+      }
+    }
+    record(st); // end of optimisation loop
+    NMPC_CUDA_CHECK(cudaGetLastError());
+  }
+
   static constexpr int kMaxThreadsPerBlock = 128;
   static constexpr bool kHasBoxQP = true;
   static constexpr size_t kQuadSmemLimit = 200 * 1024; //!< shared memory the column-split K2 may use per CTA
@@ -726,7 +826,8 @@ protected:
   cudaStream_t last_stream_ = nullptr;
   DeviceBuffer<S> x_[2], u_[2], cost_[2], deriv_, vterm_, kff_, kfb_, trace_, scal_, d_u_lo_, d_u_hi_;
   DeviceBuffer<int> ints_, d_counter_, d_fan_count_, fan_ints_;
-  DeviceBuffer<S> fan_scratch_;
+  DeviceBuffer<S> fan_scratch_, mpc_x_, mpc_u_;
+  DeviceBuffer<int> mpc_i_;
   FwdFanout<S> fan_{};
   DeviceBuffer<double> stage_in_x_, stage_in_u_, stage_out_;
   int * h_counter_ = nullptr;

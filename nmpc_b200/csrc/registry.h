@@ -33,6 +33,18 @@ public:
                      int n_u_steps,
                      bool on_device,
                      void * stream) = 0;
+  virtual void runMpc(int B,
+                      double current_t,
+                      const double * x0,
+                      const double * u_init,
+                      int n_u_steps,
+                      const nmpc_b200_mpc_config & mpc,
+                      double * x_log,
+                      double * u_log,
+                      int * iters_log,
+                      int * status_log,
+                      bool on_device,
+                      void * stream) = 0;
   virtual void get(int what, void * dst, size_t dst_bytes, bool dst_on_device, void * stream) = 0;
   virtual void sync() = 0;
   virtual void enableTiming(bool enable) = 0;

@@ -161,6 +161,39 @@ class DDPSolver:
             return None
         return self.status() == 1
 
+    def run_mpc(self, current_t, x0, u_init, n_ticks, tick_dt, plant="model", shift_inputs=True, clamp_u0=False,
+                sim_dt=None, n_substeps=1, stream=None):
+        """The reference's receding-horizon loops for B instances, every tick on the device (no host round trip):
+        solve -> apply u_list[0] -> advance current_x -> warm-start the next solve.
+
+        ``plant="model"``: current_x <- x_list[1], ``shift_inputs=True`` (TestDDPBipedal.cpp:262-267);
+        ``plant="sim"``: current_x <- stateEq(t, x, u, sim_dt) ``n_substeps`` times, usually with
+        ``shift_inputs=False, clamp_u0=True`` (TestDDPCartPole.cpp:330, :388-396).
+        Returns a dict: x [B, n_ticks+1, NX], u [B, n_ticks, NU] (applied inputs), iters, status [B, n_ticks]."""
+        self._apply_config()
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        u_init = np.ascontiguousarray(u_init, dtype=np.float64)
+        B = x0.shape[0]
+        if x0.shape != (B, self.nx) or u_init.ndim != 3 or u_init.shape[0] != B or u_init.shape[2] != self.nu:
+            raise InvalidArgument(_capi.ERR_INVALID_ARGUMENT, f"x0 must be [B, {self.nx}] and u_init [B, n_steps, {self.nu}]")
+        mc = _capi.MpcConfigStruct()
+        mc.n_ticks = int(n_ticks)
+        mc.plant = {"model": 0, "sim": 1}[plant]
+        mc.shift_inputs = int(bool(shift_inputs))
+        mc.clamp_u0 = int(bool(clamp_u0))
+        mc.n_substeps = int(n_substeps)
+        mc.tick_dt = float(tick_dt)
+        mc.sim_dt = float(tick_dt if sim_dt is None else sim_dt)
+        T = max(int(n_ticks), 0)
+        out = {"x": np.empty((B, T + 1, self.nx)), "u": np.empty((B, T, self.nu)),
+               "iters": np.empty((B, T), dtype=np.int32), "status": np.empty((B, T), dtype=np.int32)}
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib().nmpc_b200_ddp_run_mpc(self._h, B, float(current_t), vp(x0), vp(u_init), int(u_init.shape[1]),
+                                          C.byref(mc), vp(out["x"]), vp(out["u"]), vp(out["iters"]), vp(out["status"]),
+                                          0, self._stream_ptr(stream)))
+        self._B = B
+        return out
+
     def controlData(self):
         return ControlData(x_list=self._get_f64(F_X, (self._B, self._config.horizon_steps + 1, self.nx)),
                            u_list=self._get_f64(F_U, (self._B, self._config.horizon_steps, self.nu)),
