@@ -204,7 +204,8 @@ extern "C"
     int shift_inputs;
     int clamp_u0;
     int n_substeps;
-    int reserved;
+    int feedback; /* FMPC only: apply u_list[0] + coeffList().front().K (x_list[0] - current_x) at every plant sub-step
+                     (TestFmpcCartPole.cpp:351-356) */
     double tick_dt;
     double sim_dt;
   } nmpc_b200_mpc_config;
@@ -289,6 +290,29 @@ extern "C"
     NMPC_B200_FMPC_N_TRACE = 9, /* traceDataList().size()  int [B] */
     NMPC_B200_FMPC_U0 = 10 /* u_list[0]               double [B][NU] */
   } nmpc_b200_fmpc_field;
+
+  /** The FMPC loops of the reference (TestFmpcOscillator.cpp:166-190, TestFmpcCartPole.cpp:344-357 + :405-412) on
+      the device: every tick { solve(current_t, current_x, variable); u <- variable().u_list[0]; current_x <- plant;
+      variable <- fmpc_solver->variable() }.  barrier_eps_ persists from tick to tick as the member does
+      (FmpcSolver.h:413-414).  mpc->shift_inputs and mpc->clamp_u0 must be 0.  Logs (may be NULL): x_log[B][n_ticks+1][NX],
+      u_log[B][n_ticks][NU] (u_list[0]), kkt_log[B][n_ticks] (traceDataList().back().kkt_error), status_log[B][n_ticks]. */
+  int nmpc_b200_fmpc_run_mpc(nmpc_b200_fmpc * h,
+                             int B,
+                             double current_t,
+                             const double * x0,
+                             const double * x,
+                             const double * u,
+                             const double * lambda,
+                             const double * s,
+                             const double * nu,
+                             int n_steps,
+                             const nmpc_b200_mpc_config * mpc,
+                             double * x_log,
+                             double * u_log,
+                             double * kkt_log,
+                             int * status_log,
+                             int on_device,
+                             void * stream);
 
   int nmpc_b200_fmpc_get(nmpc_b200_fmpc * h, int what, void * dst, size_t dst_bytes, int dst_on_device, void * stream);
   int nmpc_b200_fmpc_sync(nmpc_b200_fmpc * h);

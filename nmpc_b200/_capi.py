@@ -59,7 +59,7 @@ class MpcConfigStruct(C.Structure):
         ("shift_inputs", C.c_int),
         ("clamp_u0", C.c_int),
         ("n_substeps", C.c_int),
-        ("reserved", C.c_int),
+        ("feedback", C.c_int),
         ("tick_dt", C.c_double),
         ("sim_dt", C.c_double),
     ]
@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "nmpc_b200_ddp_sync", "nmpc_b200_ddp_enable_timing", "nmpc_b200_ddp_get_durations", "nmpc_b200_ddp_run_mpc",
     "nmpc_b200_fmpc_config_default", "nmpc_b200_fmpc_create", "nmpc_b200_fmpc_destroy", "nmpc_b200_fmpc_set_config",
     "nmpc_b200_fmpc_solve", "nmpc_b200_fmpc_get", "nmpc_b200_fmpc_sync", "nmpc_b200_fmpc_enable_timing",
-    "nmpc_b200_fmpc_get_durations",
+    "nmpc_b200_fmpc_get_durations", "nmpc_b200_fmpc_run_mpc",
 ]
 
 _lib = None
@@ -127,6 +127,8 @@ def lib():
         L.nmpc_b200_ddp_get_durations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.nmpc_b200_fmpc_solve.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 6 + [C.c_int, C.c_int,
                                                                                                   C.c_void_p]
+        L.nmpc_b200_fmpc_run_mpc.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 6 + [C.c_int] + [
+            C.c_void_p] * 5 + [C.c_int, C.c_void_p]
         L.nmpc_b200_fmpc_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.nmpc_b200_fmpc_create.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.nmpc_b200_fmpc_destroy.argtypes = [C.c_void_p]

@@ -435,6 +435,32 @@ int nmpc_b200_fmpc_solve(nmpc_b200_fmpc * h,
   });
 }
 
+int nmpc_b200_fmpc_run_mpc(nmpc_b200_fmpc * h,
+                           int B,
+                           double current_t,
+                           const double * x0,
+                           const double * x,
+                           const double * u,
+                           const double * lambda,
+                           const double * s,
+                           const double * nu,
+                           int n_steps,
+                           const nmpc_b200_mpc_config * mpc,
+                           double * x_log,
+                           double * u_log,
+                           double * kkt_log,
+                           int * status_log,
+                           int on_device,
+                           void * stream)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_HANDLE(h);
+    if(mpc == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null mpc configuration");
+    h->engine->runMpc(B, current_t, x0, x, u, lambda, s, nu, n_steps, *mpc, x_log, u_log, kkt_log, status_log,
+                      on_device != 0, stream);
+  });
+}
+
 int nmpc_b200_fmpc_get(nmpc_b200_fmpc * h, int what, void * dst, size_t dst_bytes, int dst_on_device, void * stream)
 {
   return guarded([&] {

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "fmpc_kernels.cuh"
+#include "fmpc_mpc.cuh"
 #include "registry.h"
 
 namespace nmpc_b200
@@ -70,90 +71,115 @@ public:
              void * stream) override
   {
     DeviceGuard guard(device_);
-    const int N = cfg_.horizon_steps;
-    // checkVariable(): sequence lengths (FmpcSolver.hpp:288-312)
-    if(n_steps != N)
-    {
-      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT,
-                  "[FMPC] u_list length should be " + std::to_string(N) + " but " + std::to_string(n_steps) + ".");
-    }
-    if(B <= 0 || B > capacity_)
-    {
-      throw Error(NMPC_B200_ERR_CAPACITY,
-                  "batch " + std::to_string(B) + " outside (0, capacity " + std::to_string(capacity_) + "]");
-    }
-    if(!x0 || !x || !u || !lambda || !s || !nu) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null input array");
-    if(cfg_.enable_line_search)
-    {
-      throw Error(NMPC_B200_ERR_UNSUPPORTED,
-                  "enable_line_search (merit-function line search, FmpcSolver.hpp:755-793) is not implemented on the "
-                  "device yet");
-    }
-
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : own_stream_;
-    last_stream_ = st;
-    B_ = B;
-    ws_.B = B;
-    prm_.t0 = S(current_t);
+    cudaStream_t st = beginSolve(B, x0, x, u, lambda, s, nu, n_steps, stream);
     n_events_used_ = 0;
-    for(int & l : launches_) l = 0;
-
     record(st); // 0
-    const size_t nx1 = (size_t)(N + 1) * NX, nun = (size_t)N * NU, ngn = (size_t)N * NG;
-    const double * srcs[6] = {x0, x, u, lambda, s, nu};
-    const size_t rows[6] = {(size_t)NX, nx1, nun, nx1, ngn, ngn};
-    S * dsts[6] = {ws_.x0, ws_.x, ws_.u, ws_.lam, ws_.s, ws_.nu};
-    size_t off = 0;
-    for(int a = 0; a < 6; a++)
+    stageInputs(B, x0, x, u, lambda, s, nu, on_device, st);
+    prm_.keep_barrier_eps = 0;
+    runIterations(B, current_t, st, true);
+  }
+
+  /** The reference's FMPC loops for the whole batch, tick after tick on the device (c_api.h, fmpc_mpc.cuh). */
+  void runMpc(int B,
+              double current_t,
+              const double * x0,
+              const double * x,
+              const double * u,
+              const double * lambda,
+              const double * s,
+              const double * nu,
+              int n_steps,
+              const nmpc_b200_mpc_config & mpc,
+              double * x_log,
+              double * u_log,
+              double * kkt_log,
+              int * status_log,
+              bool on_device,
+              void * stream) override
+  {
+    DeviceGuard guard(device_);
+    if(mpc.n_ticks <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "n_ticks must be positive");
+    if(mpc.plant != 0 && mpc.plant != 1) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "plant must be 0 or 1");
+    if(mpc.plant == 1 && !ddp::HasStateEqDt<M>::value)
+      throw Error(NMPC_B200_ERR_UNSUPPORTED, "plant = 1 needs a functor with stateEq(t, x, u, dt)");
+    if(mpc.plant == 1 && mpc.n_substeps <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "n_substeps must be positive");
+    if(mpc.shift_inputs || mpc.clamp_u0)
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT,
+                  "shift_inputs / clamp_u0 have no FMPC counterpart: the Variable is passed on as it is "
+                  "(TestFmpcOscillator.cpp:189)");
+    cudaStream_t st = beginSolve(B, x0, x, u, lambda, s, nu, n_steps, stream);
+    const size_t T = mpc.n_ticks, Bp = Bp_;
+    MpcLogs<S> logs{};
+    if(x_log) logs.x = (mpc_x_.reserve((T + 1) * NX * Bp), mpc_x_.ptr);
+    if(u_log) logs.u = (mpc_u_.reserve(T * NU * Bp), mpc_u_.ptr);
+    if(kkt_log) logs.kkt = (mpc_k_.reserve(T * Bp), mpc_k_.ptr);
+    if(status_log) logs.status = (mpc_i_.reserve(T * Bp), mpc_i_.ptr);
+    ddp::MpcParams<S> mp{};
+    mp.n_ticks = mpc.n_ticks;
+    mp.plant = mpc.plant;
+    mp.n_substeps = mpc.n_substeps;
+    mp.tick_dt = S(mpc.tick_dt);
+    mp.sim_dt = S(mpc.sim_dt);
+
+    n_events_used_ = 0;
+    record(st);
+    stageInputs(B, x0, x, u, lambda, s, nu, on_device, st);
+    for(int tick = 0; tick < mpc.n_ticks; tick++)
     {
-      const double * d_src = srcs[a];
+      const double t = current_t + tick * mpc.tick_dt;
+      if(tick > 0)
+      {
+        n_events_used_ = 0;
+        record(st);
+        record(st);
+      }
+      // barrier_eps_ is a member that persists across solve() calls (FmpcSolver.h:413-414)
+      prm_.keep_barrier_eps = (tick > 0) ? 1 : 0;
+      // the non-negativity check of checkVariable() waits for the device only at the first tick; the later
+      // warm starts are the solver's own output and are checked once, after the loop
+      runIterations(B, t, st, tick == 0);
+      fmpc_mpc_advance_kernel<M><<<(B + 127) / 128, 128, 0, st>>>(model_, ws_, mp, logs, mpc.feedback, tick, S(t));
+      NMPC_CUDA_CHECK(cudaGetLastError());
+    }
+    prm_.keep_barrier_eps = 0;
+    NMPC_CUDA_CHECK(cudaMemcpyAsync(h_flag_, d_flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    auto out_f64 = [&](const S * src, double * dst, int R) {
+      if(dst == nullptr) return;
+      const size_t need = sizeof(double) * (size_t)B * R;
+      double * d_out = dst;
       if(!on_device)
       {
-        NMPC_CUDA_CHECK(
-            cudaMemcpyAsync(stage_in_.ptr + off, srcs[a], sizeof(double) * B * rows[a], cudaMemcpyHostToDevice, st));
-        d_src = stage_in_.ptr + off;
-        off += (size_t)capacity_ * rows[a];
+        if(stage_out_.bytes() < need) stage_out_.allocate(need / sizeof(double) + 1);
+        d_out = stage_out_.ptr;
       }
-      launchScatterRows<double, S>(d_src, dsts[a], B, (int)rows[a], Bp_, st);
+      launchGatherRows<S, double>(src, src, nullptr, nullptr, 0, 1, d_out, B, R, Bp_, st);
+      if(!on_device)
+      {
+        NMPC_CUDA_CHECK(cudaMemcpyAsync(dst, d_out, need, cudaMemcpyDeviceToHost, st));
+        NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+    };
+    out_f64(logs.x, x_log, (mpc.n_ticks + 1) * NX);
+    out_f64(logs.u, u_log, mpc.n_ticks * NU);
+    out_f64(logs.kkt, kkt_log, mpc.n_ticks);
+    if(status_log)
+    {
+      const size_t need = sizeof(int) * (size_t)B * mpc.n_ticks;
+      int * d_out = status_log;
+      if(!on_device)
+      {
+        if(stage_out_.bytes() < need) stage_out_.allocate(need / sizeof(double) + 1);
+        d_out = reinterpret_cast<int *>(stage_out_.ptr);
+      }
+      launchGatherRows<int, int>(logs.status, logs.status, nullptr, nullptr, 0, 1, d_out, B, mpc.n_ticks, Bp_, st);
+      if(!on_device) NMPC_CUDA_CHECK(cudaMemcpyAsync(status_log, d_out, need, cudaMemcpyDeviceToHost, st));
     }
-    record(st); // 1: inputs in device layout
-
-    const int tpb = threadsPerBlock(B);
-    const int grid = (B + tpb - 1) / tpb;
-    const int tpb1 = 128;
-    const dim3 gridN((B + tpb1 - 1) / tpb1, N), gridN1((B + tpb1 - 1) / tpb1, N + 1);
-
-    NMPC_CUDA_CHECK(cudaMemsetAsync(d_flag_.ptr, 0, sizeof(int), st));
-    fmpc_init_kernel<M><<<gridN, tpb1, 0, st>>>(model_, ws_, prm_);
-    // checkVariable(): s, nu must be non-negative (FmpcSolver.hpp:348-361) -- the reference throws, so
-    // this is the one place where solve() waits for the device
-    NMPC_CUDA_CHECK(cudaMemcpyAsync(h_flag_, d_flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+    NMPC_CUDA_CHECK(cudaGetLastError());
     if(*h_flag_ != 0)
     {
-      B_ = 0;
       throw Error(NMPC_B200_ERR_RUNTIME, "[FMPC] s_list[i] / nu_list[i] must be non-negative.");
     }
-    record(st); // 2: setup done
-
-    iter_event_base_ = n_events_used_;
-    iters_launched_ = 0;
-    for(int iter = 1; iter <= cfg_.max_iter; iter++)
-    {
-      fmpc_coeff_kernel<M><<<gridN1, tpb1, 0, st>>>(model_, ws_, prm_);
-      record(st);
-      fmpc_backward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
-      record(st);
-      fmpc_forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
-      record(st);
-      fmpc_update_kernel<M><<<gridN1, tpb1, 0, st>>>(ws_, prm_);
-      record(st);
-      for(int & l : launches_) l++;
-      iters_launched_ = iter;
-    }
-    fmpc_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws_.status, B);
-    record(st);
-    NMPC_CUDA_CHECK(cudaGetLastError());
   }
 
   void get(int what, void * dst, size_t dst_bytes, bool dst_on_device, void * stream) override
@@ -275,6 +301,120 @@ public:
   }
 
 protected:
+  /** checkVariable() sequence lengths (FmpcSolver.hpp:288-312) and per-solve bookkeeping. */
+  cudaStream_t beginSolve(int B,
+                          const double * x0,
+                          const double * x,
+                          const double * u,
+                          const double * lambda,
+                          const double * s,
+                          const double * nu,
+                          int n_steps,
+                          void * stream)
+  {
+    const int N = cfg_.horizon_steps;
+    if(n_steps != N)
+    {
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT,
+                  "[FMPC] u_list length should be " + std::to_string(N) + " but " + std::to_string(n_steps) + ".");
+    }
+    if(B <= 0 || B > capacity_)
+    {
+      throw Error(NMPC_B200_ERR_CAPACITY,
+                  "batch " + std::to_string(B) + " outside (0, capacity " + std::to_string(capacity_) + "]");
+    }
+    if(!x0 || !x || !u || !lambda || !s || !nu) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null input array");
+    if(cfg_.enable_line_search)
+    {
+      throw Error(NMPC_B200_ERR_UNSUPPORTED,
+                  "enable_line_search (merit-function line search, FmpcSolver.hpp:755-793) is not implemented on the "
+                  "device yet");
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : own_stream_;
+    last_stream_ = st;
+    B_ = B;
+    ws_.B = B;
+    return st;
+  }
+
+  void stageInputs(int B,
+                   const double * x0,
+                   const double * x,
+                   const double * u,
+                   const double * lambda,
+                   const double * s,
+                   const double * nu,
+                   bool on_device,
+                   cudaStream_t st)
+  {
+    const int N = cfg_.horizon_steps;
+    const size_t nx1 = (size_t)(N + 1) * NX, nun = (size_t)N * NU, ngn = (size_t)N * NG;
+    const double * srcs[6] = {x0, x, u, lambda, s, nu};
+    const size_t rows[6] = {(size_t)NX, nx1, nun, nx1, ngn, ngn};
+    S * dsts[6] = {ws_.x0, ws_.x, ws_.u, ws_.lam, ws_.s, ws_.nu};
+    size_t off = 0;
+    for(int a = 0; a < 6; a++)
+    {
+      const double * d_src = srcs[a];
+      if(!on_device)
+      {
+        NMPC_CUDA_CHECK(
+            cudaMemcpyAsync(stage_in_.ptr + off, srcs[a], sizeof(double) * B * rows[a], cudaMemcpyHostToDevice, st));
+        d_src = stage_in_.ptr + off;
+        off += (size_t)capacity_ * rows[a];
+      }
+      launchScatterRows<double, S>(d_src, dsts[a], B, (int)rows[a], Bp_, st);
+    }
+    record(st); // 1: inputs in device layout
+    NMPC_CUDA_CHECK(cudaMemsetAsync(d_flag_.ptr, 0, sizeof(int), st));
+  }
+
+  /** F0, then max_iter x {F1, F2, F3, F4} on the Variable resident in the workspace. */
+  void runIterations(int B, double current_t, cudaStream_t st, bool wait_for_check)
+  {
+    const int N = cfg_.horizon_steps;
+    prm_.t0 = S(current_t);
+    for(int & l : launches_) l = 0;
+    const int tpb = threadsPerBlock(B);
+    const int grid = (B + tpb - 1) / tpb;
+    const int tpb1 = 128;
+    const dim3 gridN((B + tpb1 - 1) / tpb1, N), gridN1((B + tpb1 - 1) / tpb1, N + 1);
+
+    fmpc_init_kernel<M><<<gridN, tpb1, 0, st>>>(model_, ws_, prm_);
+    if(wait_for_check)
+    {
+      // checkVariable(): s, nu must be non-negative (FmpcSolver.hpp:348-361) -- the reference throws, so
+      // this is the one place where solve() waits for the device
+      NMPC_CUDA_CHECK(cudaMemcpyAsync(h_flag_, d_flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+      NMPC_CUDA_CHECK(cudaStreamSynchronize(st));
+      if(*h_flag_ != 0)
+      {
+        B_ = 0;
+        throw Error(NMPC_B200_ERR_RUNTIME, "[FMPC] s_list[i] / nu_list[i] must be non-negative.");
+      }
+    }
+    record(st); // 2: setup done
+
+    iter_event_base_ = n_events_used_;
+    iters_launched_ = 0;
+    for(int iter = 1; iter <= cfg_.max_iter; iter++)
+    {
+      fmpc_coeff_kernel<M><<<gridN1, tpb1, 0, st>>>(model_, ws_, prm_);
+      record(st);
+      fmpc_backward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      record(st);
+      fmpc_forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      record(st);
+      fmpc_update_kernel<M><<<gridN1, tpb1, 0, st>>>(ws_, prm_);
+      record(st);
+      for(int & l : launches_) l++;
+      iters_launched_ = iter;
+    }
+    fmpc_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws_.status, B);
+    record(st);
+    NMPC_CUDA_CHECK(cudaGetLastError());
+  }
+
   static int threadsPerBlock(int B)
   {
     if(const char * env = std::getenv("NMPC_B200_TPB"))
@@ -312,6 +452,7 @@ protected:
     prm_.init_complementary_variable = cfg.init_complementary_variable;
     prm_.update_barrier_eps = cfg.update_barrier_eps;
     prm_.break_if_llt_fails = cfg.break_if_llt_fails;
+    prm_.keep_barrier_eps = 0;
     prm_.kkt_error_thre = S(cfg.kkt_error_thre);
     prm_.initial_barrier_eps = S(cfg.initial_barrier_eps);
     if(realloc_needed) allocate();
@@ -382,8 +523,8 @@ protected:
   Workspace<S> ws_{};
   cudaStream_t own_stream_ = nullptr;
   cudaStream_t last_stream_ = nullptr;
-  DeviceBuffer<S> vars_, coeff_, term_, gains_, kkt_, trace_, scal_;
-  DeviceBuffer<int> ints_, d_flag_;
+  DeviceBuffer<S> vars_, coeff_, term_, gains_, kkt_, trace_, scal_, mpc_x_, mpc_u_, mpc_k_;
+  DeviceBuffer<int> ints_, d_flag_, mpc_i_;
   DeviceBuffer<double> stage_in_, stage_out_;
   int * h_flag_ = nullptr;
   bool timing_ = false;

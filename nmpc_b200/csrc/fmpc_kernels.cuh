@@ -49,6 +49,7 @@ struct SolverParams
   int init_complementary_variable;
   int update_barrier_eps;
   int break_if_llt_fails;
+  int keep_barrier_eps; //!< MPC loop, ticks after the first: barrier_eps_ persists across solve() calls (FmpcSolver.h:413-414)
   S t0;
   S kkt_error_thre;
   S initial_barrier_eps;
@@ -133,7 +134,7 @@ __global__ void fmpc_init_kernel(const __grid_constant__ M model,
     ws.n_trace[b] = 0;
     // init_complementary_variable resets the barrier parameter (:178); otherwise the member keeps its
     // value from the previous solve() -- the engine seeds it with initial_barrier_eps
-    ws.barrier_eps[b] = prm.initial_barrier_eps;
+    if(!prm.keep_barrier_eps) ws.barrier_eps[b] = prm.initial_barrier_eps;
   }
   if(prm.init_complementary_variable)
   {

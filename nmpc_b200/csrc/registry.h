@@ -68,6 +68,22 @@ public:
                      int n_steps,
                      bool on_device,
                      void * stream) = 0;
+  virtual void runMpc(int B,
+                      double current_t,
+                      const double * x0,
+                      const double * x,
+                      const double * u,
+                      const double * lambda,
+                      const double * s,
+                      const double * nu,
+                      int n_steps,
+                      const nmpc_b200_mpc_config & mpc,
+                      double * x_log,
+                      double * u_log,
+                      double * kkt_log,
+                      int * status_log,
+                      bool on_device,
+                      void * stream) = 0;
   virtual void get(int what, void * dst, size_t dst_bytes, bool dst_on_device, void * stream) = 0;
   virtual void sync() = 0;
   virtual void enableTiming(bool enable) = 0;

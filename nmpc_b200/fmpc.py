@@ -146,6 +146,45 @@ class FmpcSolver:
         self._keep = keep
         return self.status()
 
+    def run_mpc(self, current_t, x0, var, n_ticks, tick_dt, plant="sim", sim_dt=None, n_substeps=1, feedback=False,
+                stream=None):
+        """The reference's FMPC loops for B instances with every tick on the device: solve -> u_list[0] -> plant ->
+        the Variable is the next warm start (TestFmpcOscillator.cpp:166-190); ``feedback=True`` adds
+        K_0 (x_list[0] - current_x) at every plant sub-step (TestFmpcCartPole.cpp:351-356).  barrier_eps_ persists
+        from tick to tick.  Returns dict x [B, T+1, NX], u [B, T, NU], kkt_error [B, T], status [B, T]."""
+        s = self._config.to_struct()
+        raw = bytes(s)
+        if raw != self._applied:
+            check(lib().nmpc_b200_fmpc_set_config(self._h, C.byref(s)))
+            self._applied = raw
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        N = self._config.horizon_steps
+        arrs = [x0] + [np.ascontiguousarray(a, dtype=np.float64) for a in (var.x_list, var.u_list, var.lambda_list,
+                                                                           var.s_list, var.nu_list)]
+        for name, arr, want in (("x_list", arrs[1], N + 1), ("u_list", arrs[2], N), ("lambda_list", arrs[3], N + 1),
+                                ("s_list", arrs[4], N), ("nu_list", arrs[5], N)):
+            if arr.shape[0] != B or arr.shape[1] != want:
+                raise InvalidArgument(_capi.ERR_INVALID_ARGUMENT,
+                                      f"[FMPC] {name} length should be {want} but {arr.shape[1]}.")
+        mc = _capi.MpcConfigStruct()
+        mc.n_ticks = int(n_ticks)
+        mc.plant = {"model": 0, "sim": 1}[plant]
+        mc.n_substeps = int(n_substeps)
+        mc.feedback = int(bool(feedback))
+        mc.tick_dt = float(tick_dt)
+        mc.sim_dt = float(tick_dt if sim_dt is None else sim_dt)
+        T = max(int(n_ticks), 0)
+        out = {"x": np.empty((B, T + 1, self.nx)), "u": np.empty((B, T, self.nu)), "kkt_error": np.empty((B, T)),
+               "status": np.empty((B, T), dtype=np.int32)}
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        sp = None if stream is None else C.c_void_p(getattr(stream, "cuda_stream", stream))
+        check(lib().nmpc_b200_fmpc_run_mpc(self._h, B, float(current_t), *[vp(a) for a in arrs], int(arrs[2].shape[1]),
+                                           C.byref(mc), vp(out["x"]), vp(out["u"]), vp(out["kkt_error"]),
+                                           vp(out["status"]), 0, sp))
+        self._B = B
+        return out
+
     def variable(self):
         N = self._config.horizon_steps
         v = Variable(N, self._B, self.nx, self.nu, self.ng)

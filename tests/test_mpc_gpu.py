@@ -98,3 +98,94 @@ def test_mpc_argument_errors(gpu):
         solver.run_mpc(0.0, x0, u0, n_ticks=2, tick_dt=0.01, clamp_u0=True)
     with pytest.raises(ValueError):  # initial_u_list length (DDPSolver.hpp:41-45)
         solver.run_mpc(0.0, x0, np.zeros((2, 19, 1)), n_ticks=2, tick_dt=0.01)
+
+
+def _fmpc_var(solver, B):
+    v = solver.make_variable(B)
+    v.reset(0.0, 0.0, 0.0, 1.0, 1.0)  # TestFmpcOscillator.cpp:153-154, TestFmpcCartPole.cpp:329-330
+    return v
+
+
+def _var_dict(v):
+    return {"x": v.x_list, "u": v.u_list, "lambda": v.lambda_list, "s": v.s_list, "nu": v.nu_list}
+
+
+def test_fmpc_oscillator_mpc_loop(gpu):
+    """TestFmpcOscillator.SolveMpc's loop (horizon 4 s / 0.01 s, max_iter 3, sim_dt 5 ms), first 0.6 s, for a small
+    batch of initial states; instance 0 is the test's own (0, 1).  Every tick: status Succeeded or
+    MaxIterationReached (:170), constraints hold (:180), u_list[0] and current_x track the host loop around the oracle."""
+    N, B, ticks, sim_dt = 400, 4, 120, 0.005
+    p = O.default_params("fmpc_oscillator")
+    x0 = np.array([[0.0, 1.0], [0.1, 0.8], [-0.1, 0.9], [0.05, 1.1]])
+    solver = gpu.FmpcSolver("oscillator", params=p, batch_capacity=B)
+    c = solver.config()
+    c.horizon_steps, c.max_iter = N, 3
+    got = solver.run_mpc(0.0, x0, _fmpc_var(solver, B), n_ticks=ticks, tick_dt=sim_dt, plant="sim", sim_dt=sim_dt)
+    assert set(np.unique(got["status"])) <= {1, 5}
+
+    ocfg = O.fmpc_config(horizon_steps=N, max_iter=3)
+    ovar = _var_dict(_fmpc_var(solver, B))
+    p_sim = p.copy()
+    p_sim[0] = sim_dt
+    x, t = x0.copy(), 0.0
+    for k in range(ticks):
+        r = O.fmpc_solve_batch("fmpc_oscillator", p, ocfg, x, ovar, t0=t)
+        ovar = {key: r[key] for key in ("x", "u", "lambda", "s", "nu")}
+        u = r["u"][:, 0]
+        np.testing.assert_allclose(got["x"][:, k], x, rtol=0, atol=1e-7, err_msg=f"tick {k}")
+        np.testing.assert_allclose(got["u"][:, k], u, rtol=0, atol=1e-6, err_msg=f"tick {k}")
+        assert np.array_equal(got["status"][:, k], r["status"]), f"tick {k}"
+        kkt = np.array([r["trace"][b, r["n_trace"][b] - 1, 1] for b in range(B)])
+        np.testing.assert_allclose(got["kkt_error"][:, k], kkt, rtol=1e-5, atol=1e-9, err_msg=f"tick {k}")
+        g = np.stack([-got["x"][:, k, 1] - 0.05, -got["u"][:, k, 0] - 1.0, got["u"][:, k, 0] - 0.9], axis=1)
+        assert np.all(g <= 0), (k, g)
+        x = np.stack([O.model_eval("fmpc_oscillator", p_sim, t, x[b], u[b])["x_next"] for b in range(B)])
+        t = (k + 1) * sim_dt
+    np.testing.assert_allclose(got["x"][:, ticks], x, rtol=0, atol=1e-7)
+    # the handle holds the last solve's Variable
+    np.testing.assert_allclose(solver.variable().u_list, r["u"], rtol=0, atol=1e-6)
+
+
+def test_fmpc_cartpole_mpc_loop_with_feedback(gpu):
+    """TestFmpcCartPole's loop: horizon 2 s / 0.01 s, max_iter 5, MPC tick 4 ms, plant at 2 ms with the feedback term
+    u_list[0] + K_0 (x_list[0] - current_x) at every sub-step (:351-356)."""
+    N, B, ticks = 200, 3, 25
+    mpc_dt, sim_dt = 0.004, 0.002
+    p = O.default_params("fmpc_cartpole")
+    x0 = np.array([[0.0, 0.3, 0.0, 0.0], [0.2, -0.2, 0.1, 0.0], [-0.3, 0.1, 0.0, 0.2]])
+    solver = gpu.FmpcSolver("cartpole", params=p, batch_capacity=B)
+    c = solver.config()
+    c.horizon_steps, c.max_iter = N, 5
+    got = solver.run_mpc(0.0, x0, _fmpc_var(solver, B), n_ticks=ticks, tick_dt=mpc_dt, plant="sim", sim_dt=sim_dt,
+                         n_substeps=2, feedback=True)
+
+    ocfg = O.fmpc_config(horizon_steps=N, max_iter=5)
+    ovar = _var_dict(_fmpc_var(solver, B))
+    p_sim = p.copy()
+    p_sim[0] = sim_dt
+    x, t = x0.copy(), 0.0
+    for k in range(ticks):
+        r = O.fmpc_solve_batch("fmpc_cartpole", p, ocfg, x, ovar, t0=t)
+        ovar = {key: r[key] for key in ("x", "u", "lambda", "s", "nu")}
+        np.testing.assert_allclose(got["x"][:, k], x, rtol=0, atol=1e-6, err_msg=f"tick {k}")
+        np.testing.assert_allclose(got["u"][:, k], r["u"][:, 0], rtol=1e-6, atol=1e-6, err_msg=f"tick {k}")
+        assert np.array_equal(got["status"][:, k], r["status"]), f"tick {k}"
+        K0 = r["K"][:, 0].reshape(B, 4, 1).transpose(0, 2, 1)  # column-major NU x NX
+        for _ in range(2):
+            u = r["u"][:, 0] + np.einsum("bij,bj->bi", K0, r["x"][:, 0] - x)
+            x = np.stack([O.model_eval("fmpc_cartpole", p_sim, t, x[b], u[b])["x_next"] for b in range(B)])
+        t = (k + 1) * mpc_dt
+    np.testing.assert_allclose(got["x"][:, ticks], x, rtol=0, atol=1e-6)
+
+
+def test_fmpc_mpc_argument_errors(gpu):
+    solver = gpu.FmpcSolver("oscillator", batch_capacity=2)
+    solver.config().horizon_steps = 20
+    x0 = np.array([[0.0, 1.0], [0.0, 0.9]])
+    with pytest.raises(gpu.NmpcB200Error):
+        solver.run_mpc(0.0, x0, _fmpc_var(solver, 2), n_ticks=0, tick_dt=0.005)
+    bad = _fmpc_var(solver, 2)
+    bad.s_list[1, 3, 0] = -1.0  # checkVariable (FmpcSolver.hpp:348-361)
+    with pytest.raises(gpu.NmpcB200Error) as e:
+        solver.run_mpc(0.0, x0, bad, n_ticks=2, tick_dt=0.005)
+    assert "non-negative" in str(e.value)
