@@ -324,12 +324,6 @@ protected:
                   "batch " + std::to_string(B) + " outside (0, capacity " + std::to_string(capacity_) + "]");
     }
     if(!x0 || !x || !u || !lambda || !s || !nu) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null input array");
-    if(cfg_.enable_line_search)
-    {
-      throw Error(NMPC_B200_ERR_UNSUPPORTED,
-                  "enable_line_search (merit-function line search, FmpcSolver.hpp:755-793) is not implemented on the "
-                  "device yet");
-    }
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : own_stream_;
     last_stream_ = st;
     B_ = B;
@@ -404,6 +398,7 @@ protected:
       fmpc_backward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
       record(st);
       fmpc_forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      if(cfg_.enable_line_search) fmpc_linesearch_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
       record(st);
       fmpc_update_kernel<M><<<gridN1, tpb1, 0, st>>>(ws_, prm_);
       record(st);
@@ -452,6 +447,7 @@ protected:
     prm_.init_complementary_variable = cfg.init_complementary_variable;
     prm_.update_barrier_eps = cfg.update_barrier_eps;
     prm_.break_if_llt_fails = cfg.break_if_llt_fails;
+    prm_.merit_const_scale_from_lagrange_multipliers = cfg.merit_const_scale_from_lagrange_multipliers;
     prm_.keep_barrier_eps = 0;
     prm_.kkt_error_thre = S(cfg.kkt_error_thre);
     prm_.initial_barrier_eps = S(cfg.initial_barrier_eps);

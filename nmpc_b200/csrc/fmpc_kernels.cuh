@@ -49,6 +49,7 @@ struct SolverParams
   int init_complementary_variable;
   int update_barrier_eps;
   int break_if_llt_fails;
+  int merit_const_scale_from_lagrange_multipliers;
   int keep_barrier_eps; //!< MPC loop, ticks after the first: barrier_eps_ persists across solve() calls (FmpcSolver.h:413-414)
   S t0;
   S kkt_error_thre;
@@ -809,6 +810,283 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
   ws.alpha[Bp + b] = alpha_nu_max;
   tr[3 * Bp] = alpha_s_max;
   tr[4 * Bp] = alpha_nu_max;
+}
+
+/* ----------------------------------------------------------------------------------- F3b ---- */
+/** (A.51) in Nocedal & Wright: directional derivative of |func|_1 along `dir` for one row of the Jacobian
+    (MathUtils.h:17-38); `jd` = jac.row(i) . dir. */
+template<class S>
+__device__ __forceinline__ S l1DirDerivRow(S func, S jd)
+{
+  if(func > S(0)) return jd;
+  if(func < S(0)) return S(-1) * jd;
+  return fabs(jd);
+}
+
+/** calcMeritFunc() (FmpcSolver.hpp:936-982) at variable + alpha_s * delta (x, u, s only), one thread per instance:
+    objective (running cost * dt, log barrier, terminal cost) + merit_const_scale * |constraints|_1. */
+template<class M>
+__device__ __forceinline__ typename M::Scalar fmpcMeritFunc(const M & model,
+                                                            const Workspace<typename M::Scalar> & ws,
+                                                            const SolverParams<typename M::Scalar> & prm,
+                                                            int b,
+                                                            typename M::Scalar alpha_s,
+                                                            typename M::Scalar barrier_eps,
+                                                            typename M::Scalar merit_const_scale)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  const S dt = model.dt();
+  S obj = S(0), con = S(0);
+  Matrix<S, NX, 1> x, xn;
+#pragma unroll
+  for(int d = 0; d < NX; d++)
+  {
+    const size_t o = (size_t)d * Bp + b;
+    x[d] = ws.x[o] + alpha_s * ws.dx[o];
+    con += fabs(ws.x0[o] - x[d]);
+  }
+  for(int i = 0; i < N; i++)
+  {
+    const S t = prm.t0 + i * dt;
+    Matrix<S, NU, 1> u;
+    Matrix<S, NG, 1> sv;
+#pragma unroll
+    for(int d = 0; d < NU; d++)
+    {
+      const size_t o = ((size_t)i * NU + d) * Bp + b;
+      u[d] = ws.u[o] + alpha_s * ws.du[o];
+    }
+#pragma unroll
+    for(int d = 0; d < NG; d++)
+    {
+      const size_t o = ((size_t)i * NG + d) * Bp + b;
+      sv[d] = ws.s[o] + alpha_s * ws.ds[o];
+    }
+#pragma unroll
+    for(int d = 0; d < NX; d++)
+    {
+      const size_t o = ((size_t)(i + 1) * NX + d) * Bp + b;
+      xn[d] = ws.x[o] + alpha_s * ws.dx[o];
+    }
+    obj += model.runningCost(t, x, u) * dt;
+    {
+      S log_sum = S(0);
+#pragma unroll
+      for(int d = 0; d < NG; d++) log_sum += log(sv[d]);
+      obj += S(-1) * barrier_eps * log_sum;
+    }
+    {
+      const Matrix<S, NX, 1> f = model.stateEq(t, x, u);
+      S l1 = S(0);
+#pragma unroll
+      for(int d = 0; d < NX; d++) l1 += fabs(f[d] - xn[d]);
+      con += l1;
+    }
+    {
+      const Matrix<S, NG, 1> g = model.ineqConst(t, x, u);
+      S l1 = S(0);
+#pragma unroll
+      for(int d = 0; d < NG; d++) l1 += fabs(g[d] + sv[d]);
+      con += l1;
+    }
+    x = xn;
+  }
+  obj += model.terminalCost(prm.t0 + N * dt, x);
+  return obj + merit_const_scale * con;
+}
+
+/** The line-search part of updateVariables() (FmpcSolver.hpp:755-793) with setupMeritFunc() (:837-933): Armijo
+    backtracking on alpha_s from the fraction-to-boundary value, merit function = objective + scale * l1 norm of
+    the constraints.  One thread per instance; overwrites ws.alpha[b] (alpha_s) and the trace entry. */
+template<class M>
+__global__ void fmpc_linesearch_kernel(const __grid_constant__ M model,
+                                       const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                       const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                       int iter)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
+  using L = CoeffLayout<NX, NU, NG>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= ws.B) return;
+  if(ws.status[b] != kIterationContinued) return;
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  const S dt = model.dt();
+  const S barrier_eps = ws.barrier_eps[b];
+
+  // ---- setupMeritFunc
+  S func_obj = S(0), func_con = S(0), deriv_obj = S(0), deriv_con = S(0);
+  Matrix<S, NX, 1> x, xn;
+  S dx[NX], dxn[NX];
+#pragma unroll
+  for(int d = 0; d < NX; d++)
+  {
+    const size_t o = (size_t)d * Bp + b;
+    x[d] = ws.x[o];
+    dx[d] = ws.dx[o];
+  }
+  {
+    S l1 = S(0), dd = S(0);
+#pragma unroll
+    for(int d = 0; d < NX; d++)
+    {
+      const S cf = ws.x0[(size_t)d * Bp + b] - x[d];
+      l1 += fabs(cf);
+      dd += l1DirDerivRow<S>(cf, S(-1) * dx[d]); // jacobian -I
+    }
+    func_con += l1;
+    deriv_con += dd;
+  }
+  for(int i = 0; i < N; i++)
+  {
+    const S t = prm.t0 + i * dt;
+    const S * blk = ws.coeff + (size_t)i * L::SIZE * Bp + b;
+    Matrix<S, NU, 1> u;
+    Matrix<S, NG, 1> sv;
+    S du[NU], ds[NG];
+#pragma unroll
+    for(int d = 0; d < NU; d++)
+    {
+      const size_t o = ((size_t)i * NU + d) * Bp + b;
+      u[d] = ws.u[o];
+      du[d] = ws.du[o];
+    }
+#pragma unroll
+    for(int d = 0; d < NG; d++)
+    {
+      const size_t o = ((size_t)i * NG + d) * Bp + b;
+      sv[d] = ws.s[o];
+      ds[d] = ws.ds[o];
+    }
+#pragma unroll
+    for(int d = 0; d < NX; d++)
+    {
+      const size_t o = ((size_t)(i + 1) * NX + d) * Bp + b;
+      xn[d] = ws.x[o];
+      dxn[d] = ws.dx[o];
+    }
+    {
+      // coeff.Lx, coeff.Lu are the raw running-cost gradients (FmpcSolver.hpp:421-423)
+      Matrix<S, NX, 1> Lx;
+      Matrix<S, NU, 1> Lu;
+      Matrix<S, NX, NX> Lxx;
+      Matrix<S, NU, NU> Luu;
+      Matrix<S, NX, NU> Lxu;
+      model.calcRunningCostDeriv(t, x, u, Lx, Lu, Lxx, Luu, Lxu);
+      func_obj += model.runningCost(t, x, u) * dt;
+      S a = S(0), c = S(0);
+#pragma unroll
+      for(int d = 0; d < NX; d++) a += Lx[d] * dx[d];
+#pragma unroll
+      for(int d = 0; d < NU; d++) c += Lu[d] * du[d];
+      deriv_obj += (a + c) * dt;
+    }
+    {
+      S log_sum = S(0), inv_dot = S(0);
+#pragma unroll
+      for(int d = 0; d < NG; d++)
+      {
+        log_sum += log(sv[d]);
+        inv_dot += (S(1) / sv[d]) * ds[d];
+      }
+      func_obj += S(-1) * barrier_eps * log_sum;
+      deriv_obj += S(-1) * barrier_eps * inv_dot;
+    }
+    {
+      const Matrix<S, NX, 1> f = model.stateEq(t, x, u);
+      S l1 = S(0), da = S(0), db = S(0), dn = S(0);
+#pragma unroll
+      for(int r = 0; r < NX; r++)
+      {
+        const S cf = f[r] - xn[r];
+        l1 += fabs(cf);
+        S ja = S(0), jb = S(0);
+#pragma unroll
+        for(int q = 0; q < NX; q++) ja += __ldg(blk + (size_t)(L::A + r + q * NX) * Bp) * dx[q];
+#pragma unroll
+        for(int q = 0; q < NU; q++) jb += __ldg(blk + (size_t)(L::B + r + q * NX) * Bp) * du[q];
+        da += l1DirDerivRow<S>(cf, ja);
+        db += l1DirDerivRow<S>(cf, jb);
+        dn += l1DirDerivRow<S>(cf, S(-1) * dxn[r]);
+      }
+      func_con += l1;
+      deriv_con += da;
+      deriv_con += db;
+      deriv_con += dn;
+    }
+    {
+      const Matrix<S, NG, 1> g = model.ineqConst(t, x, u);
+      S l1 = S(0), dc = S(0), dd = S(0), dsl = S(0);
+#pragma unroll
+      for(int r = 0; r < NG; r++)
+      {
+        const S cf = g[r] + sv[r];
+        l1 += fabs(cf);
+        S jc = S(0), jd = S(0);
+#pragma unroll
+        for(int q = 0; q < NX; q++) jc += __ldg(blk + (size_t)(L::C + r + q * NG) * Bp) * dx[q];
+#pragma unroll
+        for(int q = 0; q < NU; q++) jd += __ldg(blk + (size_t)(L::D + r + q * NG) * Bp) * du[q];
+        dc += l1DirDerivRow<S>(cf, jc);
+        dd += l1DirDerivRow<S>(cf, jd);
+        dsl += l1DirDerivRow<S>(cf, ds[r]);
+      }
+      func_con += l1;
+      deriv_con += dc;
+      deriv_con += dd;
+      deriv_con += dsl;
+    }
+    x = xn;
+#pragma unroll
+    for(int d = 0; d < NX; d++) dx[d] = dxn[d];
+  }
+  {
+    func_obj += model.terminalCost(prm.t0 + N * dt, x);
+    S a = S(0);
+#pragma unroll
+    for(int d = 0; d < NX; d++) a += __ldg(ws.term + (size_t)(L::T_LX + d) * Bp + b) * dx[d];
+    deriv_obj += a;
+  }
+  const S scale_min = S(1e-3);
+  S scale = scale_min;
+  if(prm.merit_const_scale_from_lagrange_multipliers)
+  {
+    // (18.32) in Nocedal & Wright
+    for(int i = 0; i <= N; i++)
+    {
+#pragma unroll
+      for(int d = 0; d < NX; d++) scale = fmax(scale, fabs(ws.lam[((size_t)i * NX + d) * Bp + b]));
+      if(i < N)
+      {
+#pragma unroll
+        for(int d = 0; d < NG; d++) scale = fmax(scale, fabs(ws.nu[((size_t)i * NG + d) * Bp + b]));
+      }
+    }
+  }
+  else
+  {
+    // (18.33) in Nocedal & Wright, rho = 0.5
+    scale = fmax(deriv_obj / ((S(1) - S(0.5)) * func_con), scale_min);
+  }
+  const S merit_func = func_obj + scale * func_con;
+  const S merit_deriv = deriv_obj + scale * deriv_con;
+
+  // ---- Armijo backtracking (:759-793)
+  const S armijo_scale = S(1e-3), update_ratio = S(0.5), alpha_s_min = S(1e-10);
+  S alpha_s = ws.alpha[b];
+  while(true)
+  {
+    if(alpha_s < alpha_s_min) break;
+    const S merit_new = fmpcMeritFunc<M>(model, ws, prm, b, alpha_s, barrier_eps, scale);
+    if(merit_new < merit_func + armijo_scale * alpha_s * merit_deriv) break;
+    alpha_s *= update_ratio;
+  }
+  ws.alpha[b] = alpha_s;
+  ws.trace[((size_t)(iter - 1) * kTraceFields + 3) * Bp + b] = alpha_s;
 }
 
 /* ------------------------------------------------------------------------------------ F4 ---- */
