@@ -368,11 +368,16 @@ def main():
                           "alg_bytes_per_launch": alg_bytes[k], "achieved_gbs": ach, "frac": ach / peak,
                           "share_of_step": med[k] / med["solve"] if med["solve"] > 0 else None}
         dominant = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"])
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
+        # same command (profiles/r1_v3_stage_kernels.md; tools/profile_kernels.sh), summed over the stage's kernels
         traffic = None
+        stage_kernels = {"derivative": ["linearize_kernel"], "backward": ["backward_kernel"],
+                         "forward": ["forward_first_kernel", "forward_fanout_kernel"]}
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and B == 4096 and args.mode == "fixed":
             try:
-                traffic = json.load(open(tpath)).get(dominant, {}).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = float(sum(tj[k]["dram_bytes_per_launch"] for k in stage_kernels[dominant]))
             except Exception:
                 traffic = None
         kernel_names = {"derivative": "ddp::linearize_kernel", "backward": "ddp::backward_kernel",

@@ -208,6 +208,24 @@ class FmpcSolver:
     def trace(self):
         return self._get_f64(F_TRACE, (self._B, self._config.max_iter, len(TRACE_FIELDS)))
 
+    def traceDataList(self, instance=0):
+        """traceDataList() of one instance (FmpcSolver.h:232-251, :337-340) as a list of dicts."""
+        tr = self.trace()[instance]
+        n = int(self.n_trace()[instance])
+        return [{"iter": int(tr[r, 0]), "kkt_error": float(tr[r, 1]), "barrier_eps": float(tr[r, 2]),
+                 "alpha_s": float(tr[r, 3]), "alpha_nu": float(tr[r, 4]), "duration_coeff": 0.0,
+                 "duration_backward": 0.0, "duration_forward": 0.0, "duration_update": 0.0} for r in range(n)]
+
+    def dumpTraceDataList(self, file_path, instance=0):
+        """Same 6-column, space-separated table as FmpcSolver::dumpTraceDataList (FmpcSolver.hpp:260-283), the format
+        nmpc_fmpc/scripts/plotFmpcTraceData.py reads.  Per-iteration durations of a batched solve are not attributed
+        to single instances: the duration columns are 0 (computationDuration() has the stage totals)."""
+        with open(file_path, "w") as f:
+            f.write("iter kkt_error duration_coeff duration_backward duration_forward duration_update\n")
+            for t in self.traceDataList(instance):
+                f.write(f"{t['iter']} {t['kkt_error']:g} {t['duration_coeff']:g} {t['duration_backward']:g} "
+                        f"{t['duration_forward']:g} {t['duration_update']:g}\n")
+
     def k_list(self):
         return self._get_f64(F_K_FF, (self._B, self._config.horizon_steps, self.nu))
 

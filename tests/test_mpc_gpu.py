@@ -189,3 +189,31 @@ def test_fmpc_mpc_argument_errors(gpu):
     with pytest.raises(gpu.NmpcB200Error) as e:
         solver.run_mpc(0.0, x0, bad, n_ticks=2, tick_dt=0.005)
     assert "non-negative" in str(e.value)
+
+
+def test_trace_dump_files_read_like_the_reference_plot_scripts(gpu, tmp_path):
+    """dumpTraceDataList() writes the tables nmpc_ddp/scripts/plotDDPTraceData.py:9-10 and its FMPC twin load with
+    np.genfromtxt(..., delimiter=' ', names=True): same header names, one row per trace entry (DDPSolver.hpp:563-598,
+    FmpcSolver.hpp:260-283)."""
+    ddp = gpu.DDPSolver("cartpole", batch_capacity=2)
+    ddp.config().max_iter = 10
+    ddp.solve_batch(0.0, O.cartpole_x0(2, 0), np.zeros((2, 100, 1)))
+    path = str(tmp_path / "ddp_trace.txt")
+    ddp.dumpTraceDataList(path, instance=1)
+    tab = np.genfromtxt(path, dtype=None, delimiter=" ", names=True)
+    assert tab.dtype.names == ("iter", "cost", "lambda", "dlambda", "alpha", "k_rel_norm", "cost_update_actual",
+                               "cost_update_expected", "cost_update_ratio", "duration_derivative", "duration_backward",
+                               "duration_forward")
+    assert len(tab) == ddp.n_trace()[1] and list(tab["iter"]) == list(range(len(tab)))
+    np.testing.assert_allclose(tab["cost"], ddp.trace()[1, :len(tab), 1], rtol=1e-5)
+
+    fm = gpu.FmpcSolver("oscillator", batch_capacity=1)
+    fm.config().horizon_steps, fm.config().max_iter = 50, 4
+    fm.solve_batch(0.0, np.array([[0.0, 1.0]]), _fmpc_var(fm, 1))
+    path = str(tmp_path / "fmpc_trace.txt")
+    fm.dumpTraceDataList(path)
+    tab = np.genfromtxt(path, dtype=None, delimiter=" ", names=True)
+    assert tab.dtype.names == ("iter", "kkt_error", "duration_coeff", "duration_backward", "duration_forward",
+                               "duration_update")
+    assert len(tab) == fm.n_trace()[0]
+    np.testing.assert_allclose(tab["kkt_error"], fm.trace()[0, :len(tab), 1], rtol=1e-5)
