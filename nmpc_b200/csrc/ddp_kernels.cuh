@@ -1231,33 +1231,57 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
   S * __restrict__ cn = dst.c;
   const size_t Bd = dst.stride, bd = dst.col;
 
-  // lane a of the group copies operands a, a+GA, ... of step `step` into ring slot `slot`
+  // Lane a of the group copies operands a, a+GA, ... of step `step` into ring slot `slot`.  The source of every
+  // operand is a RUNNING pointer that advances by its per-step stride: issue() is called for steps 0, 1, 2, ... in
+  // order, and ncu showed 18 % of this kernel's stall samples on address registers that the compiler recycled
+  // between back-to-back LDGSTS when each address was recomputed from (step, element).
+  constexpr int EPL = (O::SIZE + GA - 1) / GA; // operands per lane
+  const S * src_ptr[EPL];
+  size_t src_stride[EPL];
+#pragma unroll
+  for(int q = 0; q < EPL; q++)
+  {
+    const int e = q * GA + a;
+    if(e < O::U)
+    {
+      src_ptr[q] = xc + (size_t)(e - O::X) * Bp + b;
+      src_stride[q] = (size_t)NX * Bp;
+    }
+    else if(e < O::KFF)
+    {
+      src_ptr[q] = uc + (size_t)(e - O::U) * Bp + b;
+      src_stride[q] = (size_t)NU * Bp;
+    }
+    else if(e < O::KFB)
+    {
+      src_ptr[q] = ws.kff + (size_t)(e - O::KFF) * Bp + b;
+      src_stride[q] = (size_t)NU * Bp;
+    }
+    else
+    {
+      src_ptr[q] = ws.kfb + (size_t)((e < O::SIZE ? e : O::KFB) - O::KFB) * Bp + b;
+      src_stride[q] = (size_t)NU * NX * Bp;
+    }
+  }
   auto issue = [&](int step, int slot) {
     if(gcopy && step < N)
     {
 #pragma unroll
-      for(int e0 = 0; e0 < O::SIZE; e0 += GA)
+      for(int q = 0; q < EPL; q++)
       {
-        const int e = e0 + a;
+        const int e = q * GA + a;
         if(e < O::SIZE)
         {
-          const S * src;
-          if(e < O::U)
-            src = xc + ((size_t)step * NX + (e - O::X)) * Bp + b;
-          else if(e < O::KFF)
-            src = uc + ((size_t)step * NU + (e - O::U)) * Bp + b;
-          else if(e < O::KFB)
-            src = ws.kff + ((size_t)step * NU + (e - O::KFF)) * Bp + b;
-          else
-            src = ws.kfb + ((size_t)step * NU * NX + (e - O::KFB)) * Bp + b;
           S * rdst = ring + ((size_t)slot * O::SIZE + e) * IPW + g;
           if constexpr(sizeof(S) == 8)
-            cpAsync8(rdst, src);
+            cpAsync8(rdst, src_ptr[q]);
           else
-            cpAsync4(rdst, src);
+            cpAsync4(rdst, src_ptr[q]);
         }
       }
     }
+#pragma unroll
+    for(int q = 0; q < EPL; q++) src_ptr[q] += src_stride[q];
     cpAsyncCommit();
   };
 
@@ -1269,6 +1293,10 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
 #pragma unroll
     for(int d = 0; d < NX; d++) xn[(size_t)d * Bd + bd] = x[d];
   }
+  // running store pointers: x_{i+1}, u_i, c_i of the candidate
+  S * xs_ptr = xn + (size_t)NX * Bd + bd;
+  S * us_ptr = un + bd;
+  S * cs_ptr = cn + bd;
 
   __syncwarp(); // previous users of the ring are done
 #pragma unroll
@@ -1304,7 +1332,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
 #pragma unroll
         for(int j = 0; j < NX; j++) s += Kr[c + j * NU] * (x[j] - xr[j]);
         u[c] = (ur[c] + alpha * kr[c]) + s;
-        if(do_store) un[((size_t)i * NU + c) * Bd + bd] = u[c];
+        if(do_store) us_ptr[(size_t)c * Bd] = u[c];
       }
       const S t = prm.t0 + i * model.dt();
       const S c = model.runningCost(t, x, u);
@@ -1312,11 +1340,14 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
       if(do_store)
       {
 #pragma unroll
-        for(int d = 0; d < NX; d++) xn[((size_t)(i + 1) * NX + d) * Bd + bd] = x[d];
-        cn[(size_t)i * Bd + bd] = c;
+        for(int d = 0; d < NX; d++) xs_ptr[(size_t)d * Bd] = x[d];
+        *cs_ptr = c;
       }
       csum += c;
     }
+    xs_ptr += (size_t)NX * Bd;
+    us_ptr += (size_t)NU * Bd;
+    cs_ptr += Bd;
   }
   cpAsyncWait<0>();
   if(work)
