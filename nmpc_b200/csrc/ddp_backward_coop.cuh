@@ -45,7 +45,8 @@ struct CoopLayout
     barriers); only lanes with `work` compute.  Returns false (uniformly within the group) when the
     factorisation of Quu_F fails at some step. */
 template<class M, int GS, bool CONSTRAINED>
-__device__ __forceinline__ bool backwardSweepCoop(const Workspace<typename M::Scalar> & ws,
+__device__ __forceinline__ bool backwardSweepCoop(const M & model,
+                                                  const Workspace<typename M::Scalar> & ws,
                                                   const SolverParams<typename M::Scalar> & prm,
                                                   int b,
                                                   int j,
@@ -243,7 +244,7 @@ __device__ __forceinline__ bool backwardSweepCoop(const Workspace<typename M::Sc
           const S uv = at(blk, L::SIZE + a);
           lo[a] = ws.u_lo[a] - uv;
           hi[a] = ws.u_hi[a] - uv;
-          init[a] = (i == N - 1) ? S(0) : k_prev[a];
+          init[a] = warmStartFromNextStep<M>(model, prm.t0, i, N) ? k_prev[a] : S(0);
         }
         BoxQPResult<S, NU> qp;
         boxQpSolve<S, NU>(Quu_F, Qu, lo, hi, init, qp);
@@ -494,7 +495,7 @@ __global__ void backward_coop_kernel(const __grid_constant__ M model,
   while(__any_sync(kFull, need))
   {
     if(need) n_bwd++;
-    const bool ok = backwardSweepCoop<M, GS, CONSTRAINED>(ws, prm, b, j, us, sm, need, lambda, dV0, dV1, k_rel_norm);
+    const bool ok = backwardSweepCoop<M, GS, CONSTRAINED>(model, ws, prm, b, j, us, sm, need, lambda, dV0, dV1, k_rel_norm);
     if(need)
     {
       if(ok)

@@ -79,7 +79,8 @@ __device__ __forceinline__ int mbarTryWait(unsigned long long * bar, unsigned pa
 /** One column-split backwardPass() sweep.  All 128 threads execute every barrier; only lanes with `work` (and no
     factorisation failure so far) compute.  The return value is identical in the four warps of a lane. */
 template<class M, bool CONSTRAINED>
-__device__ __forceinline__ bool backwardSweepQuad(const Workspace<typename M::Scalar> & ws,
+__device__ __forceinline__ bool backwardSweepQuad(const M & model,
+                                                  const Workspace<typename M::Scalar> & ws,
                                                   const SolverParams<typename M::Scalar> & prm,
                                                   int b,
                                                   int lane,
@@ -353,7 +354,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const Workspace<typename M::Sc
           const S uv = u_cur[a];
           lo[a] = ws.u_lo[a] - uv;
           hi[a] = ws.u_hi[a] - uv;
-          init[a] = (i == N - 1) ? S(0) : k_prev[a];
+          init[a] = warmStartFromNextStep<M>(model, prm.t0, i, N) ? k_prev[a] : S(0);
         }
         BoxQPResult<S, NU> qp;
         boxQpSolve<S, NU>(Quu_F, Qu, lo, hi, init, qp);
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32) backward_quad_kernel(const __
   while(__syncthreads_or(need))
   {
     if(need) n_bwd++;
-    const bool ok = backwardSweepQuad<M, CONSTRAINED>(ws, prm, b, lane, w, us, sm, bars, parity, need, lambda, dV0, dV1,
+    const bool ok = backwardSweepQuad<M, CONSTRAINED>(model, ws, prm, b, lane, w, us, sm, bars, parity, need, lambda, dV0, dV1,
                                                       k_rel_norm);
     if(need)
     {

@@ -25,6 +25,9 @@
 
 #include <cuda_runtime.h>
 
+#include <type_traits>
+#include <utility>
+
 #include <nmpc_b200/matrix.h>
 
 #include "boxqp.cuh"
@@ -84,6 +87,32 @@ struct Workspace
   int * n_bwd;
   int * fan_count; //!< [1] work-list length of the phased line search (reset by K0 / K1)
 };
+
+/** Does the functor have a time-varying input dimension, `int inputDim(t)` <= NU (DDPProblem<StateDim, Eigen::Dynamic>,
+    DDPProblem.h:61-85)?  Inputs a >= inputDim(t) are padding: kept at zero by K0 and decoupled by K1. */
+template<class M, class = void>
+struct HasInputDim : std::false_type
+{
+};
+template<class M>
+struct HasInputDim<M, std::void_t<decltype(std::declval<const M &>().inputDim(std::declval<typename M::Scalar>()))>>
+: std::true_type
+{
+};
+
+/** BoxQP warm start of step i (DDPSolver.hpp:452-467): k_list_[i + 1] is used only when it has the input dimension of
+    step i; with compile-time sizes that is the case unless inputDim(t) changes between the two steps. */
+template<class M>
+__device__ __forceinline__ bool warmStartFromNextStep(const M & model, typename M::Scalar t0, int i, int N)
+{
+  if(i == N - 1) return false;
+  if constexpr(HasInputDim<M>::value)
+  {
+    const typename M::Scalar dt = model.dt();
+    return model.inputDim(t0 + i * dt) == model.inputDim(t0 + (i + 1) * dt);
+  }
+  return true;
+}
 
 template<int NX, int NU>
 struct BlockLayout
@@ -248,6 +277,20 @@ __global__ void rollout_init_kernel(const __grid_constant__ M model,
 #pragma unroll
     for(int d = 0; d < NU; d++) u[d] = ws.u[0][((size_t)i * NU + d) * Bp + b];
     const S t = prm.t0 + i * model.dt();
+    if constexpr(HasInputDim<M>::value)
+    {
+      // padding entries of initial_u_list are forced to zero; the gains keep them there
+      const int nu_act = model.inputDim(t);
+#pragma unroll
+      for(int d = 0; d < NU; d++)
+      {
+        if(d >= nu_act)
+        {
+          u[d] = S(0);
+          ws.u[0][((size_t)i * NU + d) * Bp + b] = S(0);
+        }
+      }
+    }
     const S c = model.runningCost(t, x, u);
     x = model.stateEq(t, x, u);
 #pragma unroll
@@ -323,6 +366,34 @@ __global__ void linearize_kernel(const __grid_constant__ M model,
   Matrix<S, NU, NU> Luu;
   model.calcStateEqDeriv(t, x, u, Fx, Fu);
   model.calcRunningCostDeriv(t, x, u, Lx, Lu, Lxx, Luu, Lxu);
+  if constexpr(HasInputDim<M>::value)
+  {
+    // decouple the padding inputs: Fu(:,a) = 0, Lu(a) = 0, Lxu(:,a) = 0, Luu(a,:) = Luu(:,a) = e_a.  Quu becomes
+    // block diagonal [Quu_active, 1], so k(a) = 0, K(a,:) = 0 and every active quantity equals the reference's
+    // reduced-dimension result (steps with inputDim 0 reduce to Vx = Qx, Vxx = Qxx, DDPSolver.hpp:513-517)
+    const int nu_act = model.inputDim(t);
+#pragma unroll
+    for(int a = 0; a < NU; a++)
+    {
+      if(a >= nu_act)
+      {
+#pragma unroll
+        for(int r = 0; r < NX; r++)
+        {
+          Fu(r, a) = S(0);
+          Lxu(r, a) = S(0);
+        }
+        Lu[a] = S(0);
+#pragma unroll
+        for(int c = 0; c < NU; c++)
+        {
+          Luu(a, c) = S(0);
+          Luu(c, a) = S(0);
+        }
+        Luu(a, a) = S(1);
+      }
+    }
+  }
 
   S * blk = ws.deriv + derivTileOffset<L::SIZE>(i, b, ws.Bp);
 #pragma unroll
@@ -397,7 +468,8 @@ __device__ __forceinline__ void lltSolveInPlace(const S * l, const S * invd, S *
     only lanes with `work` compute.  Returns false when the Cholesky factorisation of Quu_F failed at some
     step (LLT NumericalIssue, :500-508) -- the caller then raises lambda and sweeps again. */
 template<class M, bool CONSTRAINED>
-__device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar> & ws,
+__device__ __forceinline__ bool backwardSweep(const M & model,
+                                              const Workspace<typename M::Scalar> & ws,
                                               const SolverParams<typename M::Scalar> & prm,
                                               int b,
                                               int lane,
@@ -612,7 +684,7 @@ __device__ __forceinline__ bool backwardSweep(const Workspace<typename M::Scalar
         const S uv = u_cur[a];
         lo[a] = ws.u_lo[a] - uv;
         hi[a] = ws.u_hi[a] - uv;
-        init[a] = (i == N - 1) ? S(0) : k_prev[a];
+        init[a] = warmStartFromNextStep<M>(model, prm.t0, i, N) ? k_prev[a] : S(0);
       }
       BoxQPResult<S, NU> qp;
       boxQpSolve<S, NU>(Quu_F, Qu, lo, hi, init, qp);
@@ -837,7 +909,7 @@ __global__ void backward_kernel(const __grid_constant__ M model,
   {
     if(need) n_bwd++;
     const bool ok =
-        backwardSweep<M, CONSTRAINED>(ws, prm, b, lane, us, ring, bars, parity, need, lambda, dV0, dV1, k_rel_norm);
+        backwardSweep<M, CONSTRAINED>(model, ws, prm, b, lane, us, ring, bars, parity, need, lambda, dV0, dV1, k_rel_norm);
     if(need)
     {
       if(ok)

@@ -129,7 +129,21 @@ __global__ void mpc_advance_kernel(const __grid_constant__ M model,
 #pragma unroll
       for(int d = 0; d < NU; d++) ud[((size_t)i * NU + d) * Bp + b] = us[((size_t)(i + 1) * NU + d) * Bp + b];
     }
-    if(sel != 0)
+    // the new last entry repeats the old one (TestDDPBipedal.cpp:267) ...
+    bool repeat_last = true;
+    if constexpr(HasInputDim<M>::value)
+    {
+      // ... unless the input dimension at the new terminal time differs: then it is Zero(terminal_input_dim)
+      // (TestDDPVerticalMotion.cpp:306-315)
+      const S dt = model.dt();
+      repeat_last = model.inputDim(t + (N - 1) * dt) == model.inputDim(t + N * dt);
+    }
+    if(!repeat_last)
+    {
+#pragma unroll
+      for(int d = 0; d < NU; d++) ud[((size_t)(N - 1) * NU + d) * Bp + b] = S(0);
+    }
+    else if(sel != 0)
     {
 #pragma unroll
       for(int d = 0; d < NU; d++) ud[((size_t)(N - 1) * NU + d) * Bp + b] = us[((size_t)(N - 1) * NU + d) * Bp + b];

@@ -294,6 +294,11 @@ int oracle_model_dims(const char * model, int * nx, int * nu, int * ng, int * np
     *nx = 12, *nu = 4, *ng = 0, *nparams = DDPProblemQuadrotor::kNumParams;
     return 0;
   }
+  if(m == "vertical_motion")
+  {
+    *nx = 2, *nu = 2, *ng = 0, *nparams = DDPProblemVerticalMotion::kNumParams;
+    return 0;
+  }
   if(m == "fmpc_cartpole")
   {
     *nx = 4, *nu = 1, *ng = 4, *nparams = FmpcProblemCartPole::kNumParams;
@@ -316,6 +321,8 @@ int oracle_model_default_params(const char * model, double * params)
     DDPProblemBipedal::defaultParams(params);
   else if(m == "quadrotor")
     DDPProblemQuadrotor::defaultParams(params);
+  else if(m == "vertical_motion")
+    DDPProblemVerticalMotion::defaultParams(params);
   else if(m == "fmpc_cartpole")
     FmpcProblemCartPole::defaultParams(params);
   else if(m == "fmpc_oscillator")
@@ -360,6 +367,10 @@ int oracle_ddp_solve_batch(const char * model,
     return ddpSolveBatch<DDPProblemQuadrotor, 12, 4>(params, cfg, B, t0, x0, u_init, u_lo, u_hi, x_out, u_out,
                                                      cost_out, k_out, K_out, trace_out, n_trace_out, status_out,
                                                      iters_out, n_fwd_out, n_bwd_out, nthreads);
+  if(m == "vertical_motion")
+    return ddpSolveBatch<DDPProblemVerticalMotion, 2, 2>(params, cfg, B, t0, x0, u_init, u_lo, u_hi, x_out, u_out,
+                                                         cost_out, k_out, K_out, trace_out, n_trace_out, status_out,
+                                                         iters_out, n_fwd_out, n_bwd_out, nthreads);
   return -2;
 }
 
@@ -387,6 +398,9 @@ int oracle_model_eval(const char * model,
     return modelEval<DDPProblemBipedal, 2, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
   if(m == "quadrotor")
     return modelEval<DDPProblemQuadrotor, 12, 4>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
+  if(m == "vertical_motion")
+    return modelEval<DDPProblemVerticalMotion, 2, 2>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx,
+                                                     Vxx);
   if(m == "fmpc_cartpole")
     return modelEval<FmpcProblemCartPole, 4, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
   if(m == "fmpc_oscillator")

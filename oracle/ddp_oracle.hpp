@@ -52,6 +52,16 @@ public:
   {
     return dt_;
   }
+  /** DDPProblem::inputDim(t) (DDPProblem.h:72-85).  The reference sizes every per-step vector and matrix by it
+      (DDPProblem<StateDim, Eigen::Dynamic>); this restatement keeps fixed sizes NU = the largest dimension and treats
+      inputs a >= inputDim(t) as padding: zero in the input sequence, decoupled in the linearisation (Fu(:,a) = 0,
+      Lu(a) = 0, Lxu(:,a) = 0, Luu(a,:) = Luu(:,a) = e_a), which yields the reduced system's gains and value function
+      for the active inputs and exactly zero gains for the padding.  Pinned against the reference's own Dynamic code
+      path by tests/golden (vertical_*). */
+  virtual int inputDim(double /* t */) const
+  {
+    return NU;
+  }
 
   virtual StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const = 0; // :99
   virtual double runningCost(double t, const StateDimVector & x, const InputDimVector & u) const = 0; // :107
@@ -216,6 +226,7 @@ public:
     for(int i = 0; i < N; i++)
     {
       double t = current_t_ + i * problem_->dt();
+      for(int a = problem_->inputDim(t); a < NU; a++) control_data_.u_list[i][a] = 0.0; // padding inputs
       control_data_.x_list[i + 1] = problem_->stateEq(t, control_data_.x_list[i], control_data_.u_list[i]);
       control_data_.cost_list[i] = problem_->runningCost(t, control_data_.x_list[i], control_data_.u_list[i]);
     }
@@ -283,6 +294,21 @@ protected:
       problem_->calcStateEqDeriv(t, x, u, derivative.Fx, derivative.Fu);
       problem_->calcRunningCostDeriv(t, x, u, derivative.Lx, derivative.Lu, derivative.Lxx, derivative.Luu,
                                      derivative.Lxu);
+      for(int a = problem_->inputDim(t); a < NU; a++) // decouple the padding inputs (see DDPProblem::inputDim)
+      {
+        for(int r = 0; r < NX; r++)
+        {
+          derivative.Fu(r, a) = 0.0;
+          derivative.Lxu(r, a) = 0.0;
+        }
+        derivative.Lu[a] = 0.0;
+        for(int c = 0; c < NU; c++)
+        {
+          derivative.Luu(a, c) = 0.0;
+          derivative.Luu(c, a) = 0.0;
+        }
+        derivative.Luu(a, a) = 1.0;
+      }
     }
     double terminal_t = current_t_ + N * problem_->dt();
     problem_->calcTerminalCostDeriv(terminal_t, control_data_.x_list[N], last_Vx_, last_Vxx_);
@@ -450,9 +476,13 @@ protected:
           {
             initial_k.setZero();
           }
+          else if(problem_->inputDim(t) == problem_->inputDim(t + problem_->dt()))
+          {
+            initial_k = k_list_[i + 1]; // k_list_[i + 1].size() == input_dim (:459)
+          }
           else
           {
-            initial_k = k_list_[i + 1];
+            initial_k.setZero(); // the next step has another input dimension (:463-466)
           }
 
           // :469-480 a fresh default-configured BoxQP per step

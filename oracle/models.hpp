@@ -629,3 +629,111 @@ protected:
   F f_;
 };
 } // namespace oracle
+
+// ---- vertical motion with a time-varying input dimension (TestDDPVerticalMotion.cpp:25-234) ----
+// The functor of include/nmpc_b200/models/vertical_motion.h restates the problem bodies once for host and device;
+// what pins both is tests/golden/vertical_*: outputs of the reference's DDPSolver<2, Eigen::Dynamic> (oracle/ref).
+#include <nmpc_b200/models/vertical_motion.h>
+
+namespace oracle
+{
+/** Any host+device functor F of include/nmpc_b200/models as an oracle problem. */
+template<class F>
+class DDPProblemFromFunctor : public DDPProblem<F::NX, F::NU>
+{
+public:
+  using Base = DDPProblem<F::NX, F::NU>;
+  using StateDimVector = typename Base::StateDimVector;
+  using InputDimVector = typename Base::InputDimVector;
+  using StateStateDimMatrix = typename Base::StateStateDimMatrix;
+  using InputInputDimMatrix = typename Base::InputInputDimMatrix;
+  using StateInputDimMatrix = typename Base::StateInputDimMatrix;
+  static constexpr int kNumParams = F::NUM_PARAMS;
+  static constexpr int NX = F::NX, NU = F::NU;
+
+  explicit DDPProblemFromFunctor(const double * p) : Base(p[0]), f_(F::fromParams(p)) {}
+  static void defaultParams(double * p)
+  {
+    F::defaultParams(p);
+  }
+  template<class A, class B>
+  static void copy(const A & a, B & b, int n)
+  {
+    for(int i = 0; i < n; i++) b.d[i] = a.d[i];
+  }
+  int inputDim(double t) const override
+  {
+    return f_.inputDim(t);
+  }
+  StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    typename F::StateDimVector fx, fn;
+    typename F::InputDimVector fu;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    fn = f_.stateEq(t, fx, fu);
+    StateDimVector out;
+    copy(fn, out, NX);
+    return out;
+  }
+  double runningCost(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    typename F::StateDimVector fx;
+    typename F::InputDimVector fu;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    return f_.runningCost(t, fx, fu);
+  }
+  double terminalCost(double t, const StateDimVector & x) const override
+  {
+    typename F::StateDimVector fx;
+    copy(x, fx, NX);
+    return f_.terminalCost(t, fx);
+  }
+  void calcStateEqDeriv(double t, const StateDimVector & x, const InputDimVector & u, StateStateDimMatrix & Fx,
+                        StateInputDimMatrix & Fu) const override
+  {
+    typename F::StateDimVector fx;
+    typename F::InputDimVector fu;
+    typename F::StateStateDimMatrix a;
+    typename F::StateInputDimMatrix b;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    f_.calcStateEqDeriv(t, fx, fu, a, b);
+    copy(a, Fx, NX * NX);
+    copy(b, Fu, NX * NU);
+  }
+  void calcRunningCostDeriv(double t, const StateDimVector & x, const InputDimVector & u, StateDimVector & Lx,
+                            InputDimVector & Lu, StateStateDimMatrix & Lxx, InputInputDimMatrix & Luu,
+                            StateInputDimMatrix & Lxu) const override
+  {
+    typename F::StateDimVector fx, lx;
+    typename F::InputDimVector fu, lu;
+    typename F::StateStateDimMatrix lxx;
+    typename F::InputInputDimMatrix luu;
+    typename F::StateInputDimMatrix lxu;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    f_.calcRunningCostDeriv(t, fx, fu, lx, lu, lxx, luu, lxu);
+    copy(lx, Lx, NX);
+    copy(lu, Lu, NU);
+    copy(lxx, Lxx, NX * NX);
+    copy(luu, Luu, NU * NU);
+    copy(lxu, Lxu, NX * NU);
+  }
+  void calcTerminalCostDeriv(double t, const StateDimVector & x, StateDimVector & Vx, StateStateDimMatrix & Vxx)
+      const override
+  {
+    typename F::StateDimVector fx, vx;
+    typename F::StateStateDimMatrix vxx;
+    copy(x, fx, NX);
+    f_.calcTerminalCostDeriv(t, fx, vx, vxx);
+    copy(vx, Vx, NX);
+    copy(vxx, Vxx, NX * NX);
+  }
+
+protected:
+  F f_;
+};
+using DDPProblemVerticalMotion = DDPProblemFromFunctor<nmpc_b200::models::VerticalMotion<double>>;
+} // namespace oracle

@@ -94,3 +94,18 @@ def boxqp_solve2(H, g, lower, upper, dynamic):
     assert lib().ref_boxqp_solve2(_p(Hc), _p(g), _p(lower), _p(upper), C.c_int(int(dynamic)), _p(x),
                                   C.byref(retval)) == 0
     return x, retval.value
+
+
+def vertical_mpc(horizon_steps, with_constraint, n_ticks, x0=(1.2, 0.0), t0=0.0):
+    """TestDDPVerticalMotion's MPC loop (TestDDPVerticalMotion.cpp:236-330) with the reference's
+    DDPSolver<2, Eigen::Dynamic>: per-tick current_x, u_list[0] (padded to 2), its size, iterations; and the full
+    trajectories of the last solve (u padded to 2)."""
+    N, T = int(horizon_steps), int(n_ticks)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(2)
+    out = {"x_log": np.zeros((T, 2)), "u0_log": np.zeros((T, 2)), "dim_log": np.zeros(T, dtype=np.int32),
+           "iters_log": np.zeros(T, dtype=np.int32), "x": np.zeros((N + 1, 2)), "u": np.zeros((N, 2))}
+    rc = lib().ref_vertical_mpc(N, int(with_constraint), T, C.c_double(t0), _p(x0), _p(out["x_log"]), _p(out["u0_log"]),
+                                _p(out["dim_log"]), _p(out["iters_log"]), _p(out["x"]), _p(out["u"]))
+    if rc != 0:
+        raise RuntimeError("reference DDPSolver<2, Dynamic>::solve threw")
+    return out
