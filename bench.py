@@ -353,12 +353,17 @@ def main():
         el = algorithmic_elements(NX, NU, N_STEPS)
         peak, peak_src = measured_peaks()
         med = {k: float(np.median(v)) for k, v in stage.items()}
-        per_launch_ms = {k: med[k] / max(launches[k], 1) for k in ("derivative", "backward", "forward")}
+        # K1 fused into K2 (producer warp + consumer warp, ddp_backward_fused.cuh): no derivative launches; every
+        # backward sweep linearises its trajectory first, so the fused kernel is charged D1 + D2 per sweep
+        fused = launches["derivative"] == 0
+        stages = ("backward", "forward") if fused else ("derivative", "backward", "forward")
+        per_launch_ms = {k: med[k] / max(launches[k], 1) for k in stages}
         active_iters = float(iters.sum())
+        lin_elems = el["D1"] * (float(n_bwd.sum()) if fused else active_iters)
         alg_bytes = {
             # per launch, averaged over the launches of one solve (all B instances of this GPU)
-            "derivative": 8.0 * el["D1"] * active_iters / max(launches["derivative"], 1),
-            "backward": 8.0 * el["D2"] * float(n_bwd.sum()) / max(launches["backward"], 1),
+            "derivative": 8.0 * lin_elems / max(launches["derivative"], 1),
+            "backward": 8.0 * (el["D2"] * float(n_bwd.sum()) + (lin_elems if fused else 0.0)) / max(launches["backward"], 1),
             "forward": 8.0 * el["D3"] * float(n_fwd.sum()) / max(launches["forward"], 1),
         }
         kernels = {}
@@ -371,7 +376,8 @@ def main():
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
         # same command (profiles/r1_v3_stage_kernels.md; tools/profile_kernels.sh), summed over the stage's kernels
         traffic = None
-        stage_kernels = {"derivative": ["linearize_kernel"], "backward": ["backward_kernel"],
+        stage_kernels = {"derivative": ["linearize_kernel"],
+                         "backward": ["backward_fused_kernel"] if fused else ["backward_kernel"],
                          "forward": ["forward_first_kernel", "forward_fanout_kernel"]}
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath) and B == 4096 and args.mode == "fixed":
@@ -380,13 +386,15 @@ def main():
                 traffic = float(sum(tj[k]["dram_bytes_per_launch"] for k in stage_kernels[dominant]))
             except Exception:
                 traffic = None
-        kernel_names = {"derivative": "ddp::linearize_kernel", "backward": "ddp::backward_kernel",
+        kernel_names = {"derivative": "ddp::linearize_kernel",
+                        "backward": "ddp::backward_fused_kernel (K1 + K2: producer warp linearises, consumer warp sweeps)"
+                        if fused else "ddp::backward_kernel",
                         "forward": "ddp::forward_first_kernel + ddp::forward_fanout_kernel (one line search = 2 launches)"}
         roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": kernels[dominant]["achieved_gbs"],
                     "peak": peak, "unit": "GB/s", "frac": kernels[dominant]["frac"], "traffic": traffic,
                     "peak_source": peak_src, "kernels": kernels,
                     "whole_solve": {
-                        "alg_bytes_per_trajectory": 8.0 * (el["D0"] + (el["D1"] * active_iters + el["D2"] * float(
+                        "alg_bytes_per_trajectory": 8.0 * (el["D0"] + (lin_elems + el["D2"] * float(
                             n_bwd.sum()) + el["D3"] * float(n_fwd.sum())) / B),
                     }}
         ws = roofline["whole_solve"]
@@ -406,8 +414,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "timing": "host wall clock around K public-API calls with pinned host buffers"},
-            # per step: 2 layout + 1 rollout + 10 x (derivative, backward, 2 line-search phases) + 1 first-control extract
-            "gpu_launches": int(args.steps * (2 + 1 + 4 * MAX_ITER + 1)),
+            # per step: 2 layout + 1 rollout + 10 x ([derivative,] backward, 2 line-search phases) + 1 first-control extract
+            "gpu_launches": int(args.steps * (2 + 1 + (3 if fused else 4) * MAX_ITER + 1)),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "work": {"iterations_mean": float(iters.mean()), "forward_passes_mean": float(n_fwd.mean()),

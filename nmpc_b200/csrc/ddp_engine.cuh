@@ -19,6 +19,7 @@
 #include "ddp_kernels.cuh"
 #include "ddp_backward_coop.cuh"
 #include "ddp_backward_quad.cuh"
+#include "ddp_backward_fused.cuh"
 #include "ddp_forward_phased.cuh"
 #include "ddp_mpc.cuh"
 #include "registry.h"
@@ -470,15 +471,16 @@ protected:
     const dim3 grid1((B + tpb1 - 1) / tpb1, N + 1);
     iter_event_base_ = n_events_used_;
     iters_launched_ = 0;
+    const bool fused = backwardUsesFused(B); // Step 1 then happens inside the backward kernel
     for(int iter = 1; iter <= cfg_.max_iter; iter++)
     {
-      launchPdl(linearize_kernel<M>, grid1, dim3(tpb1), 0, st, model_, ws_, prm_);
+      if(!fused) launchPdl(linearize_kernel<M>, grid1, dim3(tpb1), 0, st, model_, ws_, prm_);
       record(st);
       launchBackward(B, tpb, grid, iter, st);
       record(st);
       launchForward(B, tpb, grid, iter, st);
       record(st);
-      launches_[1]++;
+      if(!fused) launches_[1]++;
       launches_[2]++;
       launches_[3]++;
       iters_launched_ = iter;
@@ -556,6 +558,43 @@ protected:
     launchPdl(backward_coop_kernel<M, kCoopGS, CONSTRAINED>, dim3(grid), dim3(kWarps * 32), smem, st, model_, ws_, prm_, iter);
   }
 
+  /** K1 + K2 fused (producer warp + consumer warp per 32-instance tile, ddp_backward_fused.cuh): the default while the
+      thread-per-instance sweep is the K2 variant in use, i.e. for n_x < 8.  NMPC_B200_BWD_FUSED=0 restores the
+      three-kernel pipeline. */
+  static bool backwardUsesFused(int B)
+  {
+    if(NX >= 8) return false;
+    if(const char * env = std::getenv("NMPC_B200_BWD_FUSED"))
+    {
+      if(env[0] == '0') return false;
+    }
+    if(const char * env = std::getenv("NMPC_B200_BWD_QUAD"))
+    {
+      if(env[0] == '1') return false;
+    }
+    if(const char * env = std::getenv("NMPC_B200_BWD_GS"))
+    {
+      if(std::atoi(env) > 1) return false;
+    }
+    (void)B;
+    return true;
+  }
+
+  template<bool CONSTRAINED>
+  void launchBackwardFused(int B, int iter, cudaStream_t st)
+  {
+    const size_t smem = FusedLayout<M>::bytes();
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_fused_kernel<M, CONSTRAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+      attr_set = true;
+    }
+    launchPdl(backward_fused_kernel<M, CONSTRAINED>, dim3((B + kTile - 1) / kTile), dim3(64), smem, st, model_, ws_, prm_,
+              iter);
+  }
+
   /** K2 variant for latency-bound batches: four warps per 32-instance tile (ddp_backward_quad.cuh). */
   static bool backwardUsesQuad(int B)
   {
@@ -589,6 +628,17 @@ protected:
 
   void launchBackward(int B, int tpb, int grid, int iter, cudaStream_t st)
   {
+    if constexpr(NX < 8)
+    {
+      if(backwardUsesFused(B))
+      {
+        if(cfg_.with_input_constraint)
+          launchBackwardFused<true>(B, iter, st);
+        else
+          launchBackwardFused<false>(B, iter, st);
+        return;
+      }
+    }
     if constexpr(QuadLayout<M>::bytes() <= kQuadSmemLimit)
     {
       if(backwardUsesQuad(B))

@@ -316,6 +316,55 @@ __global__ void rollout_init_kernel(const __grid_constant__ M model,
   writeTrace<S>(ws, b, 0, S(0), csum, prm.initial_lambda, prm.initial_dlambda, S(0), S(0), S(0), S(0), S(0));
 }
 
+/** procOnce() Step 1 for one (instance, step) (DDPSolver.hpp:164-176): dynamics and running-cost derivatives, with the
+    padding inputs of a time-varying input dimension decoupled. */
+template<class M>
+__device__ __forceinline__ void linearizeStep(const M & model,
+                                              typename M::Scalar t,
+                                              const Matrix<typename M::Scalar, M::NX, 1> & x,
+                                              const Matrix<typename M::Scalar, M::NU, 1> & u,
+                                              Matrix<typename M::Scalar, M::NX, M::NX> & Fx,
+                                              Matrix<typename M::Scalar, M::NX, M::NU> & Fu,
+                                              Matrix<typename M::Scalar, M::NX, 1> & Lx,
+                                              Matrix<typename M::Scalar, M::NU, 1> & Lu,
+                                              Matrix<typename M::Scalar, M::NX, M::NX> & Lxx,
+                                              Matrix<typename M::Scalar, M::NU, M::NU> & Luu,
+                                              Matrix<typename M::Scalar, M::NX, M::NU> & Lxu)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  model.calcStateEqDeriv(t, x, u, Fx, Fu);
+  model.calcRunningCostDeriv(t, x, u, Lx, Lu, Lxx, Luu, Lxu);
+  if constexpr(HasInputDim<M>::value)
+  {
+    // decouple the padding inputs: Fu(:,a) = 0, Lu(a) = 0, Lxu(:,a) = 0, Luu(a,:) = Luu(:,a) = e_a.  Quu becomes
+    // block diagonal [Quu_active, 1], so k(a) = 0, K(a,:) = 0 and every active quantity equals the reference's
+    // reduced-dimension result (steps with inputDim 0 reduce to Vx = Qx, Vxx = Qxx, DDPSolver.hpp:513-517)
+    const int nu_act = model.inputDim(t);
+#pragma unroll
+    for(int a = 0; a < NU; a++)
+    {
+      if(a >= nu_act)
+      {
+#pragma unroll
+        for(int r = 0; r < NX; r++)
+        {
+          Fu(r, a) = S(0);
+          Lxu(r, a) = S(0);
+        }
+        Lu[a] = S(0);
+#pragma unroll
+        for(int c = 0; c < NU; c++)
+        {
+          Luu(a, c) = S(0);
+          Luu(c, a) = S(0);
+        }
+        Luu(a, a) = S(1);
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------ K1 ---- */
 /** procOnce() Step 1 (DDPSolver.hpp:157-185): thread (b, i) differentiates dynamics and cost at
     (x_i, u_i) of the current trajectory; i == N evaluates the terminal cost derivatives. */
@@ -364,36 +413,7 @@ __global__ void linearize_kernel(const __grid_constant__ M model,
   Matrix<S, NX, 1> Lx;
   Matrix<S, NU, 1> Lu;
   Matrix<S, NU, NU> Luu;
-  model.calcStateEqDeriv(t, x, u, Fx, Fu);
-  model.calcRunningCostDeriv(t, x, u, Lx, Lu, Lxx, Luu, Lxu);
-  if constexpr(HasInputDim<M>::value)
-  {
-    // decouple the padding inputs: Fu(:,a) = 0, Lu(a) = 0, Lxu(:,a) = 0, Luu(a,:) = Luu(:,a) = e_a.  Quu becomes
-    // block diagonal [Quu_active, 1], so k(a) = 0, K(a,:) = 0 and every active quantity equals the reference's
-    // reduced-dimension result (steps with inputDim 0 reduce to Vx = Qx, Vxx = Qxx, DDPSolver.hpp:513-517)
-    const int nu_act = model.inputDim(t);
-#pragma unroll
-    for(int a = 0; a < NU; a++)
-    {
-      if(a >= nu_act)
-      {
-#pragma unroll
-        for(int r = 0; r < NX; r++)
-        {
-          Fu(r, a) = S(0);
-          Lxu(r, a) = S(0);
-        }
-        Lu[a] = S(0);
-#pragma unroll
-        for(int c = 0; c < NU; c++)
-        {
-          Luu(a, c) = S(0);
-          Luu(c, a) = S(0);
-        }
-        Luu(a, a) = S(1);
-      }
-    }
-  }
+  linearizeStep<M>(model, t, x, u, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu);
 
   S * blk = ws.deriv + derivTileOffset<L::SIZE>(i, b, ws.Bp);
 #pragma unroll
@@ -463,20 +483,94 @@ __device__ __forceinline__ void lltSolveInPlace(const S * l, const S * invd, S *
   }
 }
 
+__device__ __forceinline__ void mbarArrive(unsigned long long * bar)
+{
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+
+/** Where a backward sweep gets the derivative tile of step i from.  TmaFeed: K1 wrote the tiles to HBM, lane 0 fetches
+    step i-1 with one bulk (TMA) copy into a two-stage ring while step i computes. */
+template<class S, int SIZE>
+struct TmaFeed
+{
+  static constexpr bool kFused = false;
+  S * ring; //!< this warp's [2][SIZE][32] ring
+  unsigned long long * bars; //!< its two mbarriers
+  unsigned & parity;
+  const S * tile0; //!< this warp's tile of step 0 in ws.deriv
+  size_t step_stride;
+  int lane;
+  int stage;
+
+  __device__ __forceinline__ void stageStep(int st, int step)
+  {
+    if(lane == 0)
+    {
+      constexpr unsigned kStageBytes = (unsigned)(sizeof(S) * SIZE * kTile);
+      mbarExpectTx(&bars[st], kStageBytes);
+      bulkCopyG2S(ring + (size_t)st * SIZE * kTile, tile0 + (size_t)step * step_stride, kStageBytes, &bars[st]);
+    }
+  }
+  __device__ __forceinline__ void begin(int N)
+  {
+    __syncwarp(); // the previous sweep's readers are done with the ring
+    stageStep(0, N - 1);
+    stage = 0;
+  }
+  /** Tile of step i for this lane (element e at blk[e * 32]); also starts the copy of step i-1. */
+  __device__ __forceinline__ const S * acquire(int i)
+  {
+    const S * const blk = ring + (size_t)stage * SIZE * kTile + lane;
+    __syncwarp(); // every lane has finished reading the other stage (step i+1)
+    if(i > 0) stageStep(stage ^ 1, i - 1);
+    mbarWait(&bars[stage], (parity >> stage) & 1u);
+    parity ^= (1u << stage);
+    stage ^= 1;
+    return blk;
+  }
+  __device__ __forceinline__ void release() {}
+};
+
+/** ProducerFeed: no K1 and no HBM round trip -- a PRODUCER warp of the same CTA linearises step after step straight
+    into a DEPTH-stage shared-memory ring (ddp_backward_fused.cuh); full/empty mbarriers with 32 arrivals each. */
+template<class S, int SIZE, int DEPTH>
+struct ProducerFeed
+{
+  static constexpr bool kFused = true;
+  S * ring; //!< [DEPTH][SIZE][32]
+  unsigned long long * full;
+  unsigned long long * empty;
+  unsigned & fill; //!< tiles consumed so far (continues across sweeps)
+  int lane;
+
+  __device__ __forceinline__ void begin(int) {}
+  __device__ __forceinline__ const S * acquire(int)
+  {
+    const unsigned st = fill % DEPTH;
+    mbarWait(&full[st], (fill / DEPTH) & 1u);
+    return ring + (size_t)st * SIZE * kTile + lane;
+  }
+  __device__ __forceinline__ void release()
+  {
+    mbarArrive(&empty[fill % DEPTH]);
+    fill++;
+  }
+};
+
 /** One backwardPass() sweep (DDPSolver.hpp:343-534) with regularisation `lambda`, one thread per instance.
-    All 32 lanes of the warp execute the loop (lane 0 drives the TMA ring, everyone waits on its mbarriers);
-    only lanes with `work` compute.  Returns false when the Cholesky factorisation of Quu_F failed at some
-    step (LLT NumericalIssue, :500-508) -- the caller then raises lambda and sweeps again. */
-template<class M, bool CONSTRAINED>
+    All 32 lanes of the warp execute the loop (it contains the feed's barriers); only lanes with `work` compute.
+    Returns false when the Cholesky factorisation of Quu_F failed at some step (LLT NumericalIssue, :500-508) --
+    the caller then raises lambda and sweeps again. */
+template<class M, bool CONSTRAINED, class Feed>
 __device__ __forceinline__ bool backwardSweep(const M & model,
                                               const Workspace<typename M::Scalar> & ws,
                                               const SolverParams<typename M::Scalar> & prm,
                                               int b,
                                               int lane,
                                               const typename M::Scalar * __restrict__ us,
-                                              typename M::Scalar * __restrict__ ring,
-                                              unsigned long long * bars,
-                                              unsigned & parity,
+                                              const typename M::Scalar * __restrict__ xs,
+                                              Feed & feed,
                                               bool work,
                                               typename M::Scalar lambda,
                                               typename M::Scalar & dV0,
@@ -487,36 +581,39 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
   constexpr int NX = M::NX, NU = M::NU;
   using L = BlockLayout<NX, NU>;
   constexpr int tpb = kTile; // element stride inside a staged tile
-  constexpr unsigned kStageBytes = (unsigned)(sizeof(S) * L::SIZE * kTile);
   const size_t Bp = ws.Bp;
   const int N = prm.N;
 
   S Vx[NX], Vxx[NX * NX];
+  if constexpr(Feed::kFused)
+  {
+    // no K1: the terminal cost derivatives (DDPSolver.hpp:178-180) are evaluated here
+    Matrix<S, NX, 1> xN, vx;
+    Matrix<S, NX, NX> vxx;
 #pragma unroll
-  for(int d = 0; d < NX; d++) Vx[d] = ws.vterm[(size_t)d * Bp + b];
+    for(int d = 0; d < NX; d++) xN[d] = xs[((size_t)N * NX + d) * Bp + b];
+    model.calcTerminalCostDeriv(prm.t0 + N * model.dt(), xN, vx, vxx);
 #pragma unroll
-  for(int d = 0; d < NX * NX; d++) Vxx[d] = ws.vterm[(size_t)(NX + d) * Bp + b];
+    for(int d = 0; d < NX; d++) Vx[d] = vx[d];
+#pragma unroll
+    for(int d = 0; d < NX * NX; d++) Vxx[d] = vxx.d[d];
+  }
+  else
+  {
+#pragma unroll
+    for(int d = 0; d < NX; d++) Vx[d] = ws.vterm[(size_t)d * Bp + b];
+#pragma unroll
+    for(int d = 0; d < NX * NX; d++) Vxx[d] = ws.vterm[(size_t)(NX + d) * Bp + b];
+  }
 
   dV0 = S(0);
   dV1 = S(0);
   // max_i |k_i| / (|u_i| + 1) is tracked as a (numerator, denominator) pair and divided once
   S krn_num = S(0), krn_den = S(1);
 
-  // Two-stage shared-memory ring per warp.  The tile of step i-1 is fetched by one bulk (TMA) copy while
-  // step i computes, so the dependent Riccati chain never waits on HBM and no address arithmetic is spent
-  // on the 46 block entries: they are read back with immediate-offset shared loads.
-  const S * const tile0 = ws.deriv + derivTileOffset<L::SIZE>(0, b - lane, ws.Bp); // this warp's tile, step 0
-  const size_t step_stride = (size_t)(ws.Bp / kTile) * L::SIZE * kTile;
-  auto stageStep = [&](int stage, int step) {
-    if(lane == 0)
-    {
-      mbarExpectTx(&bars[stage], kStageBytes);
-      bulkCopyG2S(ring + (size_t)stage * L::SIZE * kTile, tile0 + (size_t)step * step_stride, kStageBytes, &bars[stage]);
-    }
-  };
-  __syncwarp(); // the previous sweep's readers are done with the ring
-  stageStep(0, N - 1);
-  int stage = 0;
+  // Shared-memory ring per warp (see the feeds above): the dependent Riccati chain never waits on HBM and no
+  // address arithmetic is spent on the block entries -- they are read back with immediate-offset shared loads.
+  feed.begin(N);
   S k_prev[NU]; // k_list_[i + 1], the BoxQP warm start (:452-467)
 #pragma unroll
   for(int a = 0; a < NU; a++) k_prev[a] = S(0);
@@ -531,17 +628,12 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
 
   for(int i = N - 1; i >= 0; i--)
   {
-    const S * const blk = ring + (size_t)stage * L::SIZE * kTile + lane;
-    __syncwarp(); // every lane has finished reading the other stage (step i+1)
-    if(i > 0) stageStep(stage ^ 1, i - 1);
     {
       const int ip = (i > 1) ? i - 2 : 0;
 #pragma unroll
       for(int a = 0; a < NU; a++) u_nx2[a] = us[((size_t)ip * NU + a) * Bp + b];
     }
-    mbarWait(&bars[stage], (parity >> stage) & 1u);
-    parity ^= (1u << stage);
-    stage ^= 1;
+    const S * const blk = feed.acquire(i);
     if(work && ok)
     {
       do
@@ -853,6 +945,7 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
     }
       } while(0);
     }
+    feed.release();
 #pragma unroll
     for(int a = 0; a < NU; a++)
     {
@@ -900,16 +993,19 @@ __global__ void backward_kernel(const __grid_constant__ M model,
 
   S lambda = live ? ws.lambda[b] : S(0);
   S dlambda = live ? ws.dlambda[b] : S(0);
-  const S * us = ws.u[live ? ws.sel[b] : 0];
+  const int sel = live ? ws.sel[b] : 0;
+  const S * us = ws.u[sel];
+  const S * xs = ws.x[sel];
   int n_bwd = live ? ws.n_bwd[b] : 0;
   S dV0 = S(0), dV1 = S(0), k_rel_norm = S(0);
   bool need = live;
   bool failed = false;
+  TmaFeed<S, L::SIZE> feed{ring, bars, parity, ws.deriv + derivTileOffset<L::SIZE>(0, b - lane, ws.Bp),
+                           (size_t)(ws.Bp / kTile) * L::SIZE * kTile, lane, 0};
   while(__any_sync(kFull, need))
   {
     if(need) n_bwd++;
-    const bool ok =
-        backwardSweep<M, CONSTRAINED>(model, ws, prm, b, lane, us, ring, bars, parity, need, lambda, dV0, dV1, k_rel_norm);
+    const bool ok = backwardSweep<M, CONSTRAINED>(model, ws, prm, b, lane, us, xs, feed, need, lambda, dV0, dV1, k_rel_norm);
     if(need)
     {
       if(ok)
