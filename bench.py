@@ -392,6 +392,8 @@ def main():
                         "forward": "ddp::forward_first_kernel + ddp::forward_fanout_kernel (one line search = 2 launches)"}
         roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": kernels[dominant]["achieved_gbs"],
                     "peak": peak, "unit": "GB/s", "frac": kernels[dominant]["frac"], "traffic": traffic,
+                    "model": "algorithmic bytes = SURVEY 8(d) three-stage byte model (K1+K2 fused => D1+D2 per launch); a "
+                             "fraction above 1 means the fused kernel does not move the traffic the model charges for",
                     "peak_source": peak_src, "kernels": kernels,
                     "whole_solve": {
                         "alg_bytes_per_trajectory": 8.0 * (el["D0"] + (lin_elems + el["D2"] * float(

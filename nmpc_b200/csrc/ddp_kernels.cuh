@@ -85,7 +85,7 @@ struct Workspace
   int * iters;
   int * n_fwd;
   int * n_bwd;
-  int * fan_count; //!< [1] work-list length of the phased line search (reset by K0 / K1)
+  int * fan_count; //!< [1] work-list length of the phased line search (reset by K0 / K1 / the fused K2)
 };
 
 /** Does the functor have a time-varying input dimension, `int inputDim(t)` <= NU (DDPProblem<StateDim, Eigen::Dynamic>,
@@ -271,11 +271,35 @@ __global__ void rollout_init_kernel(const __grid_constant__ M model,
   for(int d = 0; d < NX; d++) x[d] = ws.x[0][(size_t)d * Bp + b];
 
   S csum = S(0);
-  for(int i = 0; i < N; i++)
+  // initial_u_list is streamed in chunks of kChunk steps, one chunk ahead of its use: the rollout is a dependent
+  // chain, and a load issued in the step that needs it would put one HBM latency on every step
+  constexpr int kChunk = 8;
+  S ubuf[2][kChunk][NU];
+  auto loadChunk = [&](int slot, int i0) {
+#pragma unroll
+    for(int q = 0; q < kChunk; q++)
+    {
+      const int i = (i0 + q < N) ? i0 + q : N - 1;
+#pragma unroll
+      for(int d = 0; d < NU; d++) ubuf[slot][q][d] = ws.u[0][((size_t)i * NU + d) * Bp + b];
+    }
+  };
+  loadChunk(0, 0);
+  for(int i0 = 0; i0 < N; i0 += 2 * kChunk)
   {
+#pragma unroll
+    for(int half = 0; half < 2; half++)
+    {
+      loadChunk(half ^ 1, i0 + (half + 1) * kChunk);
+#pragma unroll
+      for(int q = 0; q < kChunk; q++)
+      {
+        const int i = i0 + half * kChunk + q;
+        if(i < N)
+        {
     Matrix<S, NU, 1> u;
 #pragma unroll
-    for(int d = 0; d < NU; d++) u[d] = ws.u[0][((size_t)i * NU + d) * Bp + b];
+    for(int d = 0; d < NU; d++) u[d] = ubuf[half][q][d];
     const S t = prm.t0 + i * model.dt();
     if constexpr(HasInputDim<M>::value)
     {
@@ -297,6 +321,9 @@ __global__ void rollout_init_kernel(const __grid_constant__ M model,
     for(int d = 0; d < NX; d++) ws.x[0][((size_t)(i + 1) * NX + d) * Bp + b] = x[d];
     ws.cost[0][(size_t)i * Bp + b] = c;
     csum += c;
+        }
+      }
+    }
   }
   {
     const S t = prm.t0 + N * model.dt();

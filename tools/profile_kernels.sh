@@ -1,13 +1,14 @@
 #!/bin/bash
 # ncu --set full captures of the stage kernels inside one bench.py solve (run under gpurun; ONE GPU).
 #   tools/profile_kernels.sh <tag>      -> gpurun_out/prof_<tag>_main.ncu-rep (+ optional variants)
-# The captured launches are iteration 7 of the 4th solve (3 warm-up solves x 10 iterations x 4 stage kernels skipped).
+# The captured launches are iteration 7 of the 4th solve (3 warm-up solves x 10 iterations x 3 stage kernels skipped:
+# backward_fused (K1 + K2), forward_first, forward_fanout).
 set -u
 TAG=${1:-r1}
 mkdir -p gpurun_out
 COMMON="--set full --clock-control none --import-source on"
-timeout 600 ncu $COMMON -k regex:'linearize_kernel|backward_kernel|backward_quad_kernel|forward_first_kernel|forward_fanout_kernel' \
-    --launch-skip 144 --launch-count 4 -f -o gpurun_out/prof_${TAG}_main \
+timeout 600 ncu $COMMON -k regex:'backward_fused_kernel|forward_first_kernel|forward_fanout_kernel' \
+    --launch-skip 108 --launch-count 3 -f -o gpurun_out/prof_${TAG}_main \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_${TAG}_main.log 2>&1
 if [ "${PROFILE_COOP:-0}" = "1" ]; then
   NMPC_B200_BWD_GS=4 timeout 600 ncu $COMMON -k regex:'backward_coop_kernel' --launch-skip 36 --launch-count 1 -f \
