@@ -1,6 +1,7 @@
 /* nmpc_b200 -- host side of the batched FMPC engine for one functor type M (see fmpc_kernels.cuh). */
 #pragma once
 
+#include <algorithm>
 #include <cstdlib>
 #include <memory>
 #include <vector>
@@ -374,6 +375,19 @@ protected:
     const int tpb1 = 128;
     const dim3 gridN((B + tpb1 - 1) / tpb1, N), gridN1((B + tpb1 - 1) / tpb1, N + 1);
 
+    // the sweeps run one compute warp + one loader warp per 32-instance tile (fmpc_kernels.cuh)
+    using R2 = BackwardRows<NX, NU, NG>;
+    using R3 = ForwardRows<NX, NU, NG>;
+    const int tpb2 = 64, tpb3 = 64, grid2 = (B + kTile - 1) / kTile, grid3 = grid2;
+    const size_t smem2 = R2::bytes(sizeof(S)), smem3 = R3::bytes(sizeof(S));
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+      NMPC_CUDA_CHECK(cudaFuncSetAttribute(fmpc_backward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      NMPC_CUDA_CHECK(cudaFuncSetAttribute(fmpc_forward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      attr_set = true;
+    }
+
     fmpc_init_kernel<M><<<gridN, tpb1, 0, st>>>(model_, ws_, prm_);
     if(wait_for_check)
     {
@@ -395,9 +409,9 @@ protected:
     {
       fmpc_coeff_kernel<M><<<gridN1, tpb1, 0, st>>>(model_, ws_, prm_);
       record(st);
-      fmpc_backward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      fmpc_backward_kernel<M><<<grid2, tpb2, smem2, st>>>(model_, ws_, prm_, iter);
       record(st);
-      fmpc_forward_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
+      fmpc_forward_kernel<M><<<grid3, tpb3, smem3, st>>>(model_, ws_, prm_, iter);
       if(cfg_.enable_line_search) fmpc_linesearch_kernel<M><<<grid, tpb, 0, st>>>(model_, ws_, prm_, iter);
       record(st);
       fmpc_update_kernel<M><<<gridN1, tpb1, 0, st>>>(ws_, prm_);

@@ -25,10 +25,57 @@
 
 #include <nmpc_b200/matrix.h>
 
+#include "ddp_kernels.cuh" // mbarrier / bulk-copy helpers, kTile
+
 namespace nmpc_b200
 {
 namespace fmpc
 {
+using ddp::kTile;
+
+/* The sequential sweeps F2 / F3 read ~80 scalars per instance and horizon step.  Loaded where they are used, they put
+   several dependent HBM latencies on every step of a chain that is already one warp's instruction stream; fetched with
+   per-row bulk (TMA) copies they are ~80 small TMA requests per step, which is no faster (measured: 4.4 us per step
+   either way).  Instead each 32-instance tile gets a LOADER warp next to its compute warp: the loader streams the rows
+   of step after step into a shared-memory ring with per-lane cp.async (no registers, many loads in flight, running
+   ahead by the ring depth), completion lands on a `full` mbarrier through cp.async.mbarrier.arrive.noinc (32 arrivals:
+   every lane's copies of its own column); the compute warp releases a stage on an `empty` mbarrier.  Layouts in HBM
+   stay the plain batch-innermost ones. */
+__device__ __forceinline__ void cpAsyncArriveOn(unsigned long long * bar)
+{
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
+}
+
+/** Loader side: rows 0 .. ROWS-1 of `n_fills` consecutive steps.  row_ptr[r] = address of this lane's element of row r
+    for the FIRST step, advanced by row_stride[r] (signed, in scalars) per step. */
+template<class S, int ROWS, int DEPTH>
+__device__ __forceinline__ void loaderLoop(S * ring,
+                                           unsigned long long * full,
+                                           unsigned long long * empty,
+                                           int lane,
+                                           int n_fills,
+                                           const S * (&row_ptr)[ROWS],
+                                           const long long (&row_stride)[ROWS])
+{
+  for(int f = 0; f < n_fills; f++)
+  {
+    const int st = f % DEPTH;
+    if(f >= DEPTH) ddp::mbarWait(&empty[st], (unsigned)((f / DEPTH) - 1) & 1u); // the compute warp is done with it
+    S * dst = ring + (size_t)st * ROWS * kTile + lane;
+#pragma unroll
+    for(int r = 0; r < ROWS; r++)
+    {
+      if constexpr(sizeof(S) == 8)
+        ddp::cpAsync8(dst + (size_t)r * kTile, row_ptr[r]);
+      else
+        ddp::cpAsync4(dst + (size_t)r * kTile, row_ptr[r]);
+      row_ptr[r] += row_stride[r];
+    }
+    cpAsyncArriveOn(&full[st]);
+  }
+}
+
 constexpr int kTraceFields = 5; // iter, kkt_error, barrier_eps, alpha_s, alpha_nu
 
 // FmpcSolver::Status (FmpcSolver.h:92-114)
@@ -107,6 +154,44 @@ struct CoeffLayout
   static constexpr int T_LXX = NX;
   static constexpr int T_LXBAR = NX + NX * NX;
   static constexpr int T_SIZE = NX + NX * NX + NX;
+};
+
+/** Rows staged per step by the backward sweep F2: the coefficient block, then s_i, then nu_i. */
+template<int NX, int NU, int NG>
+struct BackwardRows
+{
+  static constexpr int ROWS = CoeffLayout<NX, NU, NG>::SIZE + 2 * NG;
+  static constexpr int kDepth = 3; //!< ring stages between the loader warp and the compute warp
+  /** Shared memory of one CTA (one 32-instance tile: ring + full / empty mbarriers). */
+  static size_t bytes(size_t scalar_bytes)
+  {
+    return scalar_bytes * (size_t)kDepth * ROWS * kTile + sizeof(unsigned long long) * 2 * kDepth + 16;
+  }
+};
+
+/** Rows staged per step by the forward sweep F3: gains {P_i, s_i, K_i, k_i}, coefficients {A, B, C, D, x_bar, g_bar},
+    then s_i, nu_i of the Variable. */
+template<int NX, int NU, int NG>
+struct ForwardRows
+{
+  using L = CoeffLayout<NX, NU, NG>;
+  static constexpr int P = 0;
+  static constexpr int SV = P + NX * NX;
+  static constexpr int KFB = SV + NX;
+  static constexpr int KFF = KFB + NU * NX;
+  static constexpr int ABCD = KFF + NU; //!< rows L::A .. L::LXX-1 of the coefficient block
+  static constexpr int N_ABCD = L::LXX;
+  static constexpr int XG = ABCD + N_ABCD; //!< rows L::XBAR .. L::GBAR+NG-1
+  static constexpr int N_XG = NX + NG;
+  static constexpr int S_ = XG + N_XG;
+  static constexpr int NU_ = S_ + NG;
+  static constexpr int ROWS = NU_ + NG;
+  static constexpr int kDepth = 4; //!< an F3 step is short: let the loader run further ahead
+  /** Shared memory of one CTA (one 32-instance tile: ring + full / empty mbarriers). */
+  static size_t bytes(size_t scalar_bytes)
+  {
+    return scalar_bytes * (size_t)kDepth * ROWS * kTile + sizeof(unsigned long long) * 2 * kDepth + 16;
+  }
 };
 
 template<class S>
@@ -341,13 +426,32 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
   using L = CoeffLayout<NX, NU, NG>;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if(b >= ws.B) return;
-  if(ws.status[b] != kIterationContinued) return;
+  using R2 = BackwardRows<NX, NU, NG>;
+  constexpr unsigned kFullMask = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int any_go;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; // warp 0 computes, warp 1 loads
+  S * ring = reinterpret_cast<S *>(smem_raw); // [kDepth][ROWS][32]
+  unsigned long long * full = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(S) * (size_t)R2::kDepth * R2::ROWS * kTile);
+  unsigned long long * empty = full + R2::kDepth;
+  if(threadIdx.x == 0)
+  {
+    for(int st = 0; st < R2::kDepth; st++)
+    {
+      ddp::mbarInit(&full[st], 32);
+      ddp::mbarInit(&empty[st], 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+
+  const int b = blockIdx.x * kTile + lane; // ws.Bp is a multiple of 128: padded lanes read valid memory
   const size_t Bp = ws.Bp;
   const int N = prm.N;
   const S dt = model.dt();
-
+  bool go = (warp == 0) && (b < ws.B) && (ws.status[b < ws.B ? b : 0] == kIterationContinued);
+  S barrier_eps = S(0);
+  if(go)
+  {
   // trace entry of this iteration (:373-375)
   ws.n_trace[b] = iter;
   S * tr = ws.trace + (size_t)(iter - 1) * kTraceFields * Bp + b;
@@ -357,7 +461,7 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
   tr[4 * Bp] = S(0);
 
   // barrier parameter (:378-399): eps = clamp(0.5 * mean(s . nu), 1e-8, 1e6)
-  S barrier_eps = ws.barrier_eps[b];
+  barrier_eps = ws.barrier_eps[b];
   if(prm.update_barrier_eps)
   {
     S s_nu_ave = S(0);
@@ -384,13 +488,51 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
     if(kkt <= prm.kkt_error_thre)
     {
       ws.status[b] = kSucceeded;
-      return;
+      go = false;
     }
+  }
+  }
+  // does any instance of the tile sweep?  (also publishes the mbarrier initialisation to the loader warp)
+  if(warp == 0)
+  {
+    const bool any = __any_sync(kFullMask, go);
+    if(lane == 0) any_go = any ? 1 : 0;
+  }
+  __syncthreads();
+  if(!any_go) return;
+  if(warp == 1)
+  {
+    // loader: rows {coefficient block, s_i, nu_i} of steps N-1, N-2, ..., 0
+    const S * row_ptr[R2::ROWS];
+    long long row_stride[R2::ROWS];
+#pragma unroll
+    for(int r = 0; r < R2::ROWS; r++)
+    {
+      if(r < L::SIZE)
+      {
+        row_ptr[r] = ws.coeff + ((size_t)(N - 1) * L::SIZE + r) * Bp + b;
+        row_stride[r] = -(long long)L::SIZE * (long long)Bp;
+      }
+      else if(r < L::SIZE + NG)
+      {
+        row_ptr[r] = ws.s + ((size_t)(N - 1) * NG + (r - L::SIZE)) * Bp + b;
+        row_stride[r] = -(long long)NG * (long long)Bp;
+      }
+      else
+      {
+        row_ptr[r] = ws.nu + ((size_t)(N - 1) * NG + (r - L::SIZE - NG)) * Bp + b;
+        row_stride[r] = -(long long)NG * (long long)Bp;
+      }
+    }
+    loaderLoop<S, R2::ROWS, R2::kDepth>(ring, full, empty, lane, N, row_ptr, row_stride);
+    return;
   }
 
   // backwardPass (:524-665)
   S sv[NX], P[NX * NX];
   S nan_probe = S(0); // becomes NaN as soon as any coefficient is NaN or infinite (x * 0)
+  if(go)
+  {
 #pragma unroll
   for(int d = 0; d < NX; d++)
   {
@@ -405,33 +547,42 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
     ws.P[((size_t)N * NX * NX + d) * Bp + b] = P[d];
     nan_probe += P[d] * S(0);
   }
+  }
 
   bool llt_failed = false;
   for(int i = N - 1; i >= 0; i--)
   {
-    const S * blk = ws.coeff + (size_t)i * L::SIZE * Bp + b;
+    const int st = (N - 1 - i) % R2::kDepth;
+    const unsigned use = (unsigned)((N - 1 - i) / R2::kDepth);
+    ddp::mbarWait(&full[st], use & 1u); // operands of step i = {coefficient block, s_i, nu_i} have landed
+    if(!go)
+    {
+      ddp::mbarArrive(&empty[st]);
+      continue;
+    }
+    const S * blk = ring + (size_t)st * R2::ROWS * kTile + lane;
     S A[NX * NX], Bm[NX * NU], C[NG * NX], D[NG * NU];
 #pragma unroll
-    for(int d = 0; d < NX * NX; d++) A[d] = __ldg(blk + (size_t)(L::A + d) * Bp);
+    for(int d = 0; d < NX * NX; d++) A[d] = blk[(size_t)(L::A + d) * kTile];
 #pragma unroll
-    for(int d = 0; d < NX * NU; d++) Bm[d] = __ldg(blk + (size_t)(L::B + d) * Bp);
+    for(int d = 0; d < NX * NU; d++) Bm[d] = blk[(size_t)(L::B + d) * kTile];
 #pragma unroll
-    for(int d = 0; d < NG * NX; d++) C[d] = __ldg(blk + (size_t)(L::C + d) * Bp);
+    for(int d = 0; d < NG * NX; d++) C[d] = blk[(size_t)(L::C + d) * kTile];
 #pragma unroll
-    for(int d = 0; d < NG * NU; d++) D[d] = __ldg(blk + (size_t)(L::D + d) * Bp);
+    for(int d = 0; d < NG * NU; d++) D[d] = blk[(size_t)(L::D + d) * kTile];
     S x_bar[NX], g_bar[NG];
 #pragma unroll
-    for(int d = 0; d < NX; d++) x_bar[d] = __ldg(blk + (size_t)(L::XBAR + d) * Bp);
+    for(int d = 0; d < NX; d++) x_bar[d] = blk[(size_t)(L::XBAR + d) * kTile];
 #pragma unroll
-    for(int d = 0; d < NG; d++) g_bar[d] = __ldg(blk + (size_t)(L::GBAR + d) * Bp);
+    for(int d = 0; d < NG; d++) g_bar[d] = blk[(size_t)(L::GBAR + d) * kTile];
 
     // pre-process (:572-583)
     S nu_s[NG], tilde_sub[NG];
 #pragma unroll
     for(int j = 0; j < NG; j++)
     {
-      const S sj = ws.s[((size_t)i * NG + j) * Bp + b];
-      const S nj = ws.nu[((size_t)i * NG + j) * Bp + b];
+      const S sj = blk[(size_t)(L::SIZE + j) * kTile];
+      const S nj = blk[(size_t)(L::SIZE + NG + j) * kTile];
       nu_s[j] = nj / sj;
       tilde_sub[j] = (nu_s[j] * g_bar[j] - nj) + barrier_eps * (S(1) / sj);
     }
@@ -445,7 +596,7 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
         S acc = S(0);
 #pragma unroll
         for(int j = 0; j < NG; j++) acc += (C[j + r * NG] * nu_s[j]) * C[j + c * NG];
-        F[r + c * NX] = dt * __ldg(blk + (size_t)(L::LXX + r + c * NX) * Bp) + acc;
+        F[r + c * NX] = dt * blk[(size_t)(L::LXX + r + c * NX) * kTile] + acc;
       }
 #pragma unroll
     for(int c = 0; c < NU; c++)
@@ -456,7 +607,7 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
         S acc = S(0);
 #pragma unroll
         for(int j = 0; j < NG; j++) acc += (D[j + r * NG] * nu_s[j]) * D[j + c * NG];
-        G[r + c * NU] = dt * __ldg(blk + (size_t)(L::LUU + r + c * NU) * Bp) + acc;
+        G[r + c * NU] = dt * blk[(size_t)(L::LUU + r + c * NU) * kTile] + acc;
       }
 #pragma unroll
       for(int r = 0; r < NX; r++)
@@ -464,7 +615,7 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
         S acc = S(0);
 #pragma unroll
         for(int j = 0; j < NG; j++) acc += (C[j + r * NG] * nu_s[j]) * D[j + c * NG];
-        H[r + c * NX] = dt * __ldg(blk + (size_t)(L::LXU + r + c * NX) * Bp) + acc;
+        H[r + c * NX] = dt * blk[(size_t)(L::LXU + r + c * NX) * kTile] + acc;
       }
     }
     // Lx~ = Lx_bar + C^T tilde_sub ; Lu~ = Lu_bar + D^T tilde_sub                         (2.28f-g)
@@ -475,7 +626,7 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
       S acc = S(0);
 #pragma unroll
       for(int j = 0; j < NG; j++) acc += C[j + r * NG] * tilde_sub[j];
-      Lx_t[r] = __ldg(blk + (size_t)(L::LXBAR + r) * Bp) + acc;
+      Lx_t[r] = blk[(size_t)(L::LXBAR + r) * kTile] + acc;
     }
 #pragma unroll
     for(int r = 0; r < NU; r++)
@@ -483,7 +634,7 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
       S acc = S(0);
 #pragma unroll
       for(int j = 0; j < NG; j++) acc += D[j + r * NG] * tilde_sub[j];
-      Lu_t[r] = __ldg(blk + (size_t)(L::LUBAR + r) * Bp) + acc;
+      Lu_t[r] = blk[(size_t)(L::LUBAR + r) * kTile] + acc;
     }
     // AtP = A^T P ; F += AtP A ; H += AtP B ; BtP = B^T P ; G += BtP B                   (2.35b-d)
     S AtP[NX * NX], BtP[NU * NX];
@@ -697,9 +848,10 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
     for(int d = 0; d < NG; d++) nan_probe += g_bar[d] * S(0);
 #pragma unroll
     for(int d = 0; d < NU; d++) nan_probe += Lu_t[d] * S(0);
+    ddp::mbarArrive(&empty[st]); // the loader may refill this stage
   }
 
-  if(llt_failed || (prm.check_nan && !finite(nan_probe)))
+  if(go && (llt_failed || (prm.check_nan && !finite(nan_probe))))
   {
     ws.status[b] = kErrorInBackward;
   }
@@ -716,12 +868,99 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU, NG = M::NG;
   using L = CoeffLayout<NX, NU, NG>;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if(b >= ws.B) return;
-  if(ws.status[b] != kIterationContinued) return;
+  using R3 = ForwardRows<NX, NU, NG>;
+  constexpr unsigned kFullMask = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; // warp 0 computes, warp 1 loads
+  S * ring = reinterpret_cast<S *>(smem_raw); // [kDepth][ROWS][32]
+  unsigned long long * full = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(S) * (size_t)R3::kDepth * R3::ROWS * kTile);
+  unsigned long long * empty = full + R3::kDepth;
+  if(threadIdx.x == 0)
+  {
+    for(int st = 0; st < R3::kDepth; st++)
+    {
+      ddp::mbarInit(&full[st], 32);
+      ddp::mbarInit(&empty[st], 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+
+  const int b = blockIdx.x * kTile + lane; // ws.Bp is a multiple of 128: padded lanes read valid memory
+  const bool go = (b < ws.B) && (ws.status[b < ws.B ? b : 0] == kIterationContinued);
+  // both warps see the same 32 verdicts: uniform exit; the barrier also publishes the mbarrier initialisation
+  if(!__syncthreads_or(go)) return;
   const size_t Bp = ws.Bp;
   const int N = prm.N;
-  const S barrier_eps = ws.barrier_eps[b];
+  if(warp == 1)
+  {
+    // loader: rows of ForwardRows for steps 0, 1, ..., N; step N needs only P_N and s_N (the other rows of that
+    // stage repeat step N - 1: their pointers stop advancing there)
+    const S * row_ptr[R3::ROWS];
+    long long row_stride[R3::ROWS];
+#pragma unroll
+    for(int r = 0; r < R3::ROWS; r++)
+    {
+      if(r < R3::SV)
+      {
+        row_ptr[r] = ws.P + (size_t)(r - R3::P) * Bp + b;
+        row_stride[r] = (long long)(NX * NX) * (long long)Bp;
+      }
+      else if(r < R3::KFB)
+      {
+        row_ptr[r] = ws.sv + (size_t)(r - R3::SV) * Bp + b;
+        row_stride[r] = (long long)NX * (long long)Bp;
+      }
+      else if(r < R3::KFF)
+      {
+        row_ptr[r] = ws.kfb + (size_t)(r - R3::KFB) * Bp + b;
+        row_stride[r] = (long long)(NU * NX) * (long long)Bp;
+      }
+      else if(r < R3::ABCD)
+      {
+        row_ptr[r] = ws.kff + (size_t)(r - R3::KFF) * Bp + b;
+        row_stride[r] = (long long)NU * (long long)Bp;
+      }
+      else if(r < R3::XG)
+      {
+        row_ptr[r] = ws.coeff + (size_t)(L::A + (r - R3::ABCD)) * Bp + b;
+        row_stride[r] = (long long)L::SIZE * (long long)Bp;
+      }
+      else if(r < R3::S_)
+      {
+        row_ptr[r] = ws.coeff + (size_t)(L::XBAR + (r - R3::XG)) * Bp + b;
+        row_stride[r] = (long long)L::SIZE * (long long)Bp;
+      }
+      else if(r < R3::NU_)
+      {
+        row_ptr[r] = ws.s + (size_t)(r - R3::S_) * Bp + b;
+        row_stride[r] = (long long)NG * (long long)Bp;
+      }
+      else
+      {
+        row_ptr[r] = ws.nu + (size_t)(r - R3::NU_) * Bp + b;
+        row_stride[r] = (long long)NG * (long long)Bp;
+      }
+    }
+    loaderLoop<S, R3::ROWS, R3::kDepth>(ring, full, empty, lane, N, row_ptr, row_stride); // steps 0 .. N-1
+#pragma unroll
+    for(int r = R3::KFB; r < R3::ROWS; r++) row_ptr[r] -= row_stride[r]; // step N: everything but P, s repeats N-1
+    {
+      const int f = N, st = f % R3::kDepth;
+      if(f >= R3::kDepth) ddp::mbarWait(&empty[st], (unsigned)((f / R3::kDepth) - 1) & 1u);
+      S * dst = ring + (size_t)st * R3::ROWS * kTile + lane;
+#pragma unroll
+      for(int r = 0; r < R3::ROWS; r++)
+      {
+        if constexpr(sizeof(S) == 8)
+          ddp::cpAsync8(dst + (size_t)r * kTile, row_ptr[r]);
+        else
+          ddp::cpAsync4(dst + (size_t)r * kTile, row_ptr[r]);
+      }
+      cpAsyncArriveOn(&full[st]);
+    }
+    return;
+  }
+  const S barrier_eps = go ? ws.barrier_eps[b] : S(0);
 
   S dx[NX];
 #pragma unroll
@@ -732,21 +971,28 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
   const S margin_ratio = S(0.995);
   for(int i = 0; i <= N; i++)
   {
+    const int st = i % R3::kDepth;
+    ddp::mbarWait(&full[st], (unsigned)(i / R3::kDepth) & 1u); // operands of step i (ForwardRows) have landed
+    if(!go)
+    {
+      ddp::mbarArrive(&empty[st]);
+      continue;
+    }
+    const S * op = ring + (size_t)st * R3::ROWS * kTile + lane;
     // dlambda_i = P_i dx_i - s_i                                                    (2.33)
 #pragma unroll
     for(int r = 0; r < NX; r++)
     {
       S acc = S(0);
 #pragma unroll
-      for(int q = 0; q < NX; q++) acc += __ldg(ws.P + ((size_t)i * NX * NX + r + q * NX) * Bp + b) * dx[q];
-      const S dl = acc - __ldg(ws.sv + ((size_t)i * NX + r) * Bp + b);
+      for(int q = 0; q < NX; q++) acc += op[(size_t)(R3::P + r + q * NX) * kTile] * dx[q];
+      const S dl = acc - op[(size_t)(R3::SV + r) * kTile];
       ws.dlam[((size_t)i * NX + r) * Bp + b] = dl;
       ws.dx[((size_t)i * NX + r) * Bp + b] = dx[r];
       nan_probe += dl * S(0) + dx[r] * S(0);
     }
     if(i == N) break;
 
-    const S * blk = ws.coeff + (size_t)i * L::SIZE * Bp + b;
     // du_i = K_i dx_i + k_i                                                         (2.36)
     S du[NU];
 #pragma unroll
@@ -754,8 +1000,8 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
     {
       S acc = S(0);
 #pragma unroll
-      for(int q = 0; q < NX; q++) acc += __ldg(ws.kfb + ((size_t)i * NU * NX + r + q * NU) * Bp + b) * dx[q];
-      du[r] = acc + __ldg(ws.kff + ((size_t)i * NU + r) * Bp + b);
+      for(int q = 0; q < NX; q++) acc += op[(size_t)(R3::KFB + r + q * NU) * kTile] * dx[q];
+      du[r] = acc + op[(size_t)(R3::KFF + r) * kTile];
       ws.du[((size_t)i * NU + r) * Bp + b] = du[r];
       nan_probe += du[r] * S(0);
     }
@@ -765,12 +1011,12 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
     {
       S cdx = S(0), ddu = S(0);
 #pragma unroll
-      for(int q = 0; q < NX; q++) cdx += __ldg(blk + (size_t)(L::C + j + q * NG) * Bp) * dx[q];
+      for(int q = 0; q < NX; q++) cdx += op[(size_t)(R3::ABCD + L::C + j + q * NG) * kTile] * dx[q];
 #pragma unroll
-      for(int q = 0; q < NU; q++) ddu += __ldg(blk + (size_t)(L::D + j + q * NG) * Bp) * du[q];
-      const S dsj = S(-1) * ((cdx + ddu) + __ldg(blk + (size_t)(L::GBAR + j) * Bp));
-      const S sj = ws.s[((size_t)i * NG + j) * Bp + b];
-      const S nj = ws.nu[((size_t)i * NG + j) * Bp + b];
+      for(int q = 0; q < NU; q++) ddu += op[(size_t)(R3::ABCD + L::D + j + q * NG) * kTile] * du[q];
+      const S dsj = S(-1) * ((cdx + ddu) + op[(size_t)(R3::XG + NX + j) * kTile]);
+      const S sj = op[(size_t)(R3::S_ + j) * kTile];
+      const S nj = op[(size_t)(R3::NU_ + j) * kTile];
       const S dnj = S(-1) * (nj * (dsj + sj) - barrier_eps) / sj;
       ws.ds[((size_t)i * NG + j) * Bp + b] = dsj;
       ws.dnu[((size_t)i * NG + j) * Bp + b] = dnj;
@@ -786,15 +1032,17 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
     {
       S adx = S(0), bdu = S(0);
 #pragma unroll
-      for(int q = 0; q < NX; q++) adx += __ldg(blk + (size_t)(L::A + r + q * NX) * Bp) * dx[q];
+      for(int q = 0; q < NX; q++) adx += op[(size_t)(R3::ABCD + L::A + r + q * NX) * kTile] * dx[q];
 #pragma unroll
-      for(int q = 0; q < NU; q++) bdu += __ldg(blk + (size_t)(L::B + r + q * NX) * Bp) * du[q];
-      dxn[r] = (adx + bdu) + __ldg(blk + (size_t)(L::XBAR + r) * Bp);
+      for(int q = 0; q < NU; q++) bdu += op[(size_t)(R3::ABCD + L::B + r + q * NX) * kTile] * du[q];
+      dxn[r] = (adx + bdu) + op[(size_t)(R3::XG + r) * kTile];
     }
 #pragma unroll
     for(int r = 0; r < NX; r++) dx[r] = dxn[r];
+    ddp::mbarArrive(&empty[st]); // the loader may refill this stage
   }
 
+  if(!go) return;
   S * tr = ws.trace + (size_t)(iter - 1) * kTraceFields * Bp + b;
   if(prm.check_nan && !finite(nan_probe))
   {

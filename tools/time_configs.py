@@ -65,7 +65,11 @@ def fmpc():
     var = s.make_variable(B)
     var.reset(0.0, 0.0, 0.0, 1.0, 1.0)
     t = best_of(lambda: s.solve_batch(0.0, x0, var), s.synchronize)
-    return {"fmpc_cartpole": {"batch": B, "horizon": N, "iters": 10, "ms": 1e3 * t, "solves_per_s": B / t}}
+    s.enable_timing(True)
+    s.solve_batch(0.0, x0, var)
+    d = s.computationDuration()
+    return {"fmpc_cartpole": {"batch": B, "horizon": N, "iters": 10, "ms": 1e3 * t, "solves_per_s": B / t,
+                              "stage_ms": {k: v for k, v in d.items() if isinstance(v, float)}}}
 
 
 if __name__ == "__main__":
