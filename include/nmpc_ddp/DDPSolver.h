@@ -200,6 +200,34 @@ public:
     computation_duration_.forward = ms[5];
   }
 
+  /** \brief The receding-horizon loops that call solve() every tick in the reference (TestDDPBipedal.cpp:243-268,
+      TestDDPCartPole.cpp:313-343 + :388-396), for B instances, every tick on the device (nmpc_b200_ddp_run_mpc).
+      x0[B][StateDim], u_init[B][n_steps][InputDim]; logs (may be null): x_log[B][n_ticks+1][StateDim],
+      u_log[B][n_ticks][InputDim], iters_log[B][n_ticks], status_log[B][n_ticks].  Afterwards get() / controlData()
+      describe the last tick's solve. */
+  void runMpc(int B,
+              double current_t,
+              const double * x0,
+              const double * u_init,
+              int n_steps,
+              const nmpc_b200_mpc_config & mpc,
+              double * x_log,
+              double * u_log,
+              int * iters_log = nullptr,
+              int * status_log = nullptr)
+  {
+    ensureHandle();
+    if(config_.with_input_constraint || mpc.clamp_u0)
+    {
+      if(!input_limits_func_) throw std::runtime_error("[DDP] input limits function is not set.");
+      const auto limits = input_limits_func_(current_t);
+      nmpc_b200::throwOnError(nmpc_b200_ddp_set_input_limits(handle_, limits[0].d, limits[1].d));
+    }
+    nmpc_b200::throwOnError(nmpc_b200_ddp_run_mpc(handle_, B, current_t, x0, u_init, n_steps, &mpc, x_log, u_log,
+                                                  iters_log, status_log, 0, nullptr));
+    last_B_ = B;
+  }
+
   /** \brief Copy a result field of the last solveBatch() (see nmpc_b200_ddp_field). */
   void get(int field, void * dst, size_t bytes) const
   {

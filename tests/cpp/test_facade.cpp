@@ -92,6 +92,34 @@ int main(int argc, char ** argv)
   bool again = ddp_solver->solve(0.0, current_x, ddp_solver->controlData().u_list);
   std::printf("ddp_warm_iters %d %d\n", ddp_solver->traceDataList().back().iter, again ? 1 : 0);
 
+  // the test's MPC loop (TestDDPCartPole.cpp:313-343 + :388-396) for a batch of 2, 5 ticks on the device:
+  // max_iter 3, input limits +-15 N, plant at sim_dt = 2 ms twice per 4 ms tick, applied input clamped
+  {
+    auto mpc_solver = std::make_shared<nmpc_ddp::DDPSolver<4, 1>>(ddp_problem, 2);
+    mpc_solver->config().horizon_steps = 200;
+    mpc_solver->config().max_iter = 3;
+    mpc_solver->config().with_input_constraint = true;
+    mpc_solver->setInputLimitsFunc([](double) {
+      std::array<DDPProblemCartPole::InputDimVector, 2> limits;
+      limits[0][0] = -15.0;
+      limits[1][0] = 15.0;
+      return limits;
+    });
+    nmpc_b200_mpc_config mpc{};
+    mpc.n_ticks = 5, mpc.plant = 1, mpc.shift_inputs = 0, mpc.clamp_u0 = 1, mpc.n_substeps = 2;
+    mpc.tick_dt = 0.004, mpc.sim_dt = 0.002;
+    const double x0[8] = {0, M_PI, 0, 0, 0.5, 2.0, 0, 0};
+    std::vector<double> u_init(2 * 200, 0.0), x_log(2 * 6 * 4), u_log(2 * 5);
+    std::vector<int> iters(2 * 5);
+    mpc_solver->runMpc(2, 0.0, x0, u_init.data(), 200, mpc, x_log.data(), u_log.data(), iters.data());
+    std::printf("mpc_u");
+    for(double v : u_log) std::printf(" %.17g", v);
+    std::printf("\nmpc_x_final");
+    for(int b = 0; b < 2; b++)
+      for(int d = 0; d < 4; d++) std::printf(" %.17g", x_log[(b * 6 + 5) * 4 + d]);
+    std::printf("\n");
+  }
+
   // wrong initial_u_list length => std::invalid_argument (DDPSolver.hpp:41-45)
   try
   {

@@ -62,6 +62,24 @@ def test_facade_against_oracle(facade_bin, gpu):
                       "cost_update_expected", "cost_update_ratio", "duration_derivative", "duration_backward",
                       "duration_forward"]  # the columns scripts/plotDDPTraceData.py reads
 
+    # runMpc: 5 ticks of TestDDPCartPole's loop for 2 instances vs the same loop driven from here around the oracle
+    lo, hi = np.array([-15.0]), np.array([15.0])
+    cfg = O.ddp_config(horizon_steps=200, max_iter=3, with_input_constraint=1)
+    p_sim = p.copy()
+    p_sim[0] = 0.002
+    xs, us = np.array([[0, np.pi, 0, 0], [0.5, 2.0, 0, 0]]), np.zeros((2, 200, 1))
+    applied = []
+    for k in range(5):
+        r = O.ddp_solve_batch("cartpole", p, cfg, xs, us, t0=k * 0.004, u_lo=lo, u_hi=hi)
+        ua = np.clip(r["u"][:, 0], lo, hi)
+        applied.append(ua[:, 0])
+        for _ in range(2):
+            xs = np.stack([O.model_eval("cartpole", p_sim, 0.0, xs[b], ua[b])["x_next"] for b in range(2)])
+        us = r["u"].copy()
+    mpc_u = np.array([float(v) for v in d["mpc_u"].split()]).reshape(2, 5)
+    np.testing.assert_allclose(mpc_u, np.array(applied).T, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(np.array([float(v) for v in d["mpc_x_final"].split()]).reshape(2, 4), xs, rtol=0, atol=1e-9)
+
     var = {"x": np.zeros((1, 101, 4)), "u": np.zeros((1, 100, 1)), "lambda": np.zeros((1, 101, 4)),
            "s": np.ones((1, 100, 4)), "nu": np.ones((1, 100, 4))}
     fref = O.fmpc_solve_batch("fmpc_cartpole", O.default_params("fmpc_cartpole"), O.fmpc_config(max_iter=5), x0, var)
