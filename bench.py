@@ -17,7 +17,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# Same setting torchrun applies to every rank of an N > 1 run: without it the BLAS / OpenMP worker pools that numpy and
+# torch start at import compete with the thread that enqueues the solve (measured on the B200 box: e2e 1.93 ms per
+# step with the pools, 1.83 ms without; the device-timed `value` is unaffected).  The CPU arms are not throttled by
+# it: they pass their thread count to the oracle explicitly (host_threads()).
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
