@@ -24,7 +24,12 @@ namespace nmpc_b200
 {
 namespace ddp
 {
-constexpr int kFusedDepth = 4; //!< ring stages between producer and consumer
+#ifndef NMPC_B200_FUSED_DEPTH
+#  define NMPC_B200_FUSED_DEPTH 2
+#endif
+/** Ring stages between producer and consumer.  The ring (11.8 KB per stage for cart-pole) caps the CTAs per SM at
+    large batch: 4 stages -> 4 CTAs per SM by shared memory, 2 stages -> 5 (then registers bound). */
+constexpr int kFusedDepth = NMPC_B200_FUSED_DEPTH;
 
 template<class M>
 struct FusedLayout
