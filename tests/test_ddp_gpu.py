@@ -256,3 +256,47 @@ def test_constrained_batch_parity(gpu):
     assert np.array_equal(K == 0, ref["K"] == 0), "clamped sets differ"
     assert _rel_u(solver.controlData().u_list, ref["u"]).max() <= U_TOL_REF
     assert np.max(np.abs(solver.cost() - ref["cost"]) / np.abs(ref["cost"])) <= COST_TOL_REF
+
+
+@pytest.mark.parametrize("mode", ["ref", "fixed"])
+def test_full_size_batches_are_independent_of_the_kernel_variant(gpu, mode):
+    """BASELINE.json configs[1] (B = 4096) and a config-5 sweep point (B = 65536, which takes the large-batch line
+    search kernel and many CTAs per SM), through size-independent properties:
+      * instances never interact, so the first 512 instances solved ALONE (small-batch kernel variants, verified
+        against the oracle above) must give bit-identical trajectories, costs and counters inside the big batches;
+      * a sample of the big batch against the oracle;
+      * every accepted step lowers the cost (trace), iteration counters within bounds."""
+    kw = dict(max_iter=10)
+    if mode == "fixed":
+        kw.update(k_rel_norm_thre=0.0, cost_update_thre=0.0)
+    N, sub = 100, 512
+    p = O.default_params("cartpole")
+    small = gpu.DDPSolver("cartpole", params=p, batch_capacity=sub)
+    for k, v in kw.items():
+        setattr(small.config(), k, v)
+    x0_all = O.cartpole_x0(65536, 65536)
+    small.solve_batch(0.0, x0_all[:sub], np.zeros((sub, N, 1)))
+    want_u, want_cost = small.controlData().u_list, small.cost()
+    want_it, want_fwd = small.iterations(), small.n_forward()
+    ref = O.ddp_solve_batch("cartpole", p, O.ddp_config(horizon_steps=N, **kw), x0_all[:64], np.zeros((64, N, 1)))
+    for B in (4096, 65536):
+        big = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+        for k, v in kw.items():
+            setattr(big.config(), k, v)
+        big.solve_batch(0.0, x0_all[:B], np.zeros((B, N, 1)))
+        u = big.controlData().u_list
+        np.testing.assert_array_equal(u[:sub], want_u)
+        np.testing.assert_array_equal(big.cost()[:sub], want_cost)
+        np.testing.assert_array_equal(big.iterations()[:sub], want_it)
+        np.testing.assert_array_equal(big.n_forward()[:sub], want_fwd)
+        assert _rel_u(u[:64], ref["u"]).max() <= (U_TOL_REF if mode == "ref" else U_TOL_FIXED)
+        assert np.array_equal(big.iterations()[:64], ref["iters"])
+        it = big.iterations()
+        assert it.min() >= 1 and it.max() <= 10 and (mode == "ref" or np.all(it == 10))
+        tr = big.trace()  # [B, 11, 9]: rows of accepted steps carry a lower cost than the row before
+        cost_rows = tr[:, :, 1]
+        for r in range(1, 11):
+            accepted = (tr[:, r, 4] > 0) & (tr[:, r, 6] > 0) & (r <= it)  # alpha set and cost_update_actual > 0
+            assert np.all(cost_rows[accepted, r] < cost_rows[accepted, r - 1])
+        assert np.isfinite(big.cost()).all()
+        big.close()
