@@ -47,7 +47,7 @@ struct FusedLayout
 
 /** Producer side of one sweep: tiles of steps N-1 ... 0 for this lane's instance. */
 template<class M>
-__device__ __forceinline__ void produceSweep(const M & model,
+__device__ __forceinline__ void produceSweep(const M & model_in_constant_bank,
                                              const Workspace<typename M::Scalar> & ws,
                                              const SolverParams<typename M::Scalar> & prm,
                                              int b,
@@ -62,6 +62,8 @@ __device__ __forceinline__ void produceSweep(const M & model,
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
   using L = BlockLayout<NX, NU>;
+  const M model = model_in_constant_bank; // out of the kernel-parameter constant bank, once (see forwardRolloutRing)
+  const S t0 = prm.t0;
   const size_t Bp = ws.Bp;
   const int N = prm.N;
 
@@ -92,7 +94,7 @@ __device__ __forceinline__ void produceSweep(const M & model,
     Matrix<S, NX, 1> Lx;
     Matrix<S, NU, 1> Lu;
     Matrix<S, NU, NU> Luu;
-    linearizeStep<M>(model, prm.t0 + i * model.dt(), x, u, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu);
+    linearizeStep<M>(model, t0 + i * model.dt(), x, u, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu);
 
     const unsigned st = fill % kFusedDepth;
     if(fill >= (unsigned)kFusedDepth) mbarWait(&empty[st], ((fill / kFusedDepth) - 1u) & 1u); // the consumer is done with it

@@ -610,6 +610,7 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
   constexpr int tpb = kTile; // element stride inside a staged tile
   const size_t Bp = ws.Bp;
   const int N = prm.N;
+  const int reg_type = prm.reg_type; // loop-invariant solver constants out of the constant bank, once
 
   S Vx[NX], Vxx[NX * NX];
   if constexpr(Feed::kFused)
@@ -748,7 +749,7 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
 
     // regularisation (:421-441)
     S Qux_reg[NU * NX], Quu_F[NU * NU];
-    if(prm.reg_type == 2)
+    if(reg_type == 2)
     {
       // Vxx_reg = Vxx + lambda I  =>  Tu_reg = Tu + lambda Fu^T
       S Tur[NU * NX];
@@ -783,7 +784,7 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
       for(int d = 0; d < NU * NX; d++) Qux_reg[d] = Qux[d];
 #pragma unroll
       for(int d = 0; d < NU * NU; d++) Quu_F[d] = Quu[d];
-      if(prm.reg_type == 1)
+      if(reg_type == 1)
       {
 #pragma unroll
         for(int a = 0; a < NU; a++) Quu_F[a + a * NU] += lambda;
@@ -1399,7 +1400,7 @@ __device__ __forceinline__ FwdDest<S> candidateBuffer(const Workspace<S> & ws, i
 }
 
 template<class M, int GA, int DEPTH>
-__device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model,
+__device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model_in_constant_bank,
                                                                  const Workspace<typename M::Scalar> & ws,
                                                                  const SolverParams<typename M::Scalar> & prm,
                                                                  typename M::Scalar * __restrict__ ring,
@@ -1417,6 +1418,10 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
   constexpr int NX = M::NX, NU = M::NU;
   using O = FwdOperands<NX, NU>;
   constexpr int IPW = 32 / GA;
+  // the functor and the few solver constants of the step loop, copied out of the kernel-parameter constant bank once:
+  // read in place they were re-fetched every step (ncu: LDC c[0x0][..] among the top stall sites of the rollout)
+  const M model = model_in_constant_bank;
+  const S t0 = prm.t0;
   const size_t Bp = ws.Bp;
   const int N = prm.N;
   const S * __restrict__ xc = ws.x[sel];
@@ -1529,7 +1534,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
         u[c] = (ur[c] + alpha * kr[c]) + s;
         if(do_store) us_ptr[(size_t)c * Bd] = u[c];
       }
-      const S t = prm.t0 + i * model.dt();
+      const S t = t0 + i * model.dt();
       const S c = model.runningCost(t, x, u);
       x = model.stateEq(t, x, u);
       if(do_store)
@@ -1547,7 +1552,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
   cpAsyncWait<0>();
   if(work)
   {
-    const S t = prm.t0 + N * model.dt();
+    const S t = t0 + N * model.dt();
     const S c = model.terminalCost(t, x);
     if(do_store) cn[(size_t)N * Bd + bd] = c;
     csum += c;
