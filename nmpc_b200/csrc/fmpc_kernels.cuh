@@ -1021,9 +1021,13 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
       ws.ds[((size_t)i * NG + j) * Bp + b] = dsj;
       ws.dnu[((size_t)i * NG + j) * Bp + b] = dnj;
       nan_probe += dsj * S(0) + dnj * S(0);
-      // fraction-to-boundary (:729-736)
-      if(dsj < S(0)) alpha_s_max = fmin(alpha_s_max, S(-1) * margin_ratio * sj / dsj);
-      if(dnj < S(0)) alpha_nu_max = fmin(alpha_nu_max, S(-1) * margin_ratio * nj / dnj);
+      // fraction-to-boundary (:729-736).  The quotients are formed unconditionally and selected afterwards: same
+      // values where they are used, but the 2 x NG divisions of a step become independent instruction streams the
+      // scheduler can interleave instead of NG x 2 branches with a dependent division each
+      const S cand_s = S(-1) * margin_ratio * sj / dsj;
+      const S cand_nu = S(-1) * margin_ratio * nj / dnj;
+      alpha_s_max = (dsj < S(0)) ? fmin(alpha_s_max, cand_s) : alpha_s_max;
+      alpha_nu_max = (dnj < S(0)) ? fmin(alpha_nu_max, cand_nu) : alpha_nu_max;
     }
     // dx_{i+1} = A dx_i + B du_i + x_bar                                             (2.26b)
     S dxn[NX];
