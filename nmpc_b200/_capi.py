@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libnmpc_b200.so")
+# NMPC_B200_LIBRARY: load another build of the same library (kernel-variant experiments); the default is the in-tree one
+_LIB_PATH = os.environ.get("NMPC_B200_LIBRARY") or os.path.join(_HERE, "libnmpc_b200.so")
 
 OK = 0
 ERR_INVALID_ARGUMENT = 1

@@ -1,4 +1,5 @@
-/* nmpc_b200 -- K2 for latency-bound batches: the four warps of a CTA split one 32-instance tile by COLUMNS.
+/* nmpc_b200 -- K2 for latency-bound batches: the W warps of a CTA (W = 4 ... 12, one matrix column each where possible)
+ * split one 32-instance tile by COLUMNS.
  *
  * With one thread per instance a backward step is ~540 instructions (425 of them fp64, two issue cycles each)
  * along one warp's instruction stream, and a 4096-instance batch offers only 128 such warps to 592 warp
@@ -31,14 +32,17 @@ namespace nmpc_b200
 {
 namespace ddp
 {
-constexpr int kQuadWarps = 4;
 
 template<class M>
 struct QuadLayout
 {
   static constexpr int NX = M::NX, NU = M::NU;
   using L = BlockLayout<NX, NU>;
-  static constexpr int CPW = (NX + kQuadWarps - 1) / kQuadWarps; //!< matrix columns per warp
+  /** Warps that share one 32-instance tile: one matrix column per warp up to 12 warps (measured on the quadrotor,
+      n_x = 12, B = 8192: 11.6 / 8.9 / 8.5 ms per 10 sweeps with 4 / 6 / 12 warps -- fewer instructions per warp and
+      three warps per scheduler to hide each other's latency), never fewer than 4. */
+  static constexpr int W = (NX >= 12) ? 12 : (NX < 4 ? 4 : NX);
+  static constexpr int CPW = (NX + W - 1) / W; //!< matrix columns per warp
   // shared-memory regions, in elements of [32 lanes]
   static constexpr int RING = 0; //!< 2 stages of the derivative tile
   static constexpr int TX = RING + 2 * L::SIZE; //!< Tx [c + j*NX]
@@ -50,7 +54,7 @@ struct QuadLayout
   static constexpr int VX = VN + NX * NX; //!< Vx' [j]
   /** Large tiles (n_x >= 8) keep the warp's own columns of Vxx and Qxx in shared memory instead of registers:
       Qxx(:,c) is parked in the VN region (its final home after the K terms are added), Vxx(:,c) in VXXC. */
-  static constexpr bool kColsInSmem = (NX * CPW > 16);
+  static constexpr bool kColsInSmem = (NX >= 8);
   static constexpr int VXXC = VX + NX; //!< own columns of Vxx [r + c*NX] (private to the owning warp)
   static constexpr int ELEMS = VXXC + (kColsInSmem ? NX * NX : 0);
   static constexpr size_t bytes()
@@ -115,7 +119,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const M & model,
 #pragma unroll
   for(int cc = 0; cc < CPW; cc++)
   {
-    const int c = w + cc * kQuadWarps;
+    const int c = w + cc * Q::W;
 #pragma unroll
     for(int r = 0; r < NX; r++)
     {
@@ -196,7 +200,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const M & model,
 #pragma unroll
       for(int cc = 0; cc < CPW; cc++)
       {
-        const int c = w + cc * kQuadWarps;
+        const int c = w + cc * Q::W;
         if(c < NX)
         {
           S vcol[NX];
@@ -297,7 +301,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const M & model,
 #pragma unroll
       for(int cc = 0; cc < CPW; cc++)
       {
-        const int c = w + cc * kQuadWarps;
+        const int c = w + cc * Q::W;
         if(c < NX)
         {
           S fxc[NX];
@@ -459,7 +463,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const M & model,
 #pragma unroll
         for(int cc = 0; cc < CPW; cc++)
         {
-          const int c = w + cc * kQuadWarps;
+          const int c = w + cc * Q::W;
           if(c < NX)
           {
             S ktq[NU];
@@ -507,7 +511,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const M & model,
 #pragma unroll
       for(int cc = 0; cc < CPW; cc++)
       {
-        const int c = w + cc * kQuadWarps;
+        const int c = w + cc * Q::W;
         if(c < NX)
         {
 #pragma unroll
@@ -561,7 +565,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const M & model,
 #pragma unroll
       for(int cc = 0; cc < CPW; cc++)
       {
-        const int c = w + cc * kQuadWarps;
+        const int c = w + cc * Q::W;
         if(c < NX)
         {
 #pragma unroll
@@ -591,7 +595,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const M & model,
 
 /** procOnce() Step 2 (DDPSolver.hpp:188-231), four warps per 32-instance tile. */
 template<class M, bool CONSTRAINED>
-__global__ void __launch_bounds__(kQuadWarps * 32) backward_quad_kernel(const __grid_constant__ M model,
+__global__ void __launch_bounds__(QuadLayout<M>::W * 32) backward_quad_kernel(const __grid_constant__ M model,
                                                                         const __grid_constant__ Workspace<typename M::Scalar> ws,
                                                                         const __grid_constant__ SolverParams<typename M::Scalar> prm,
                                                                         int iter)

@@ -622,7 +622,7 @@ protected:
                                            (int)smem));
       attr_set = true;
     }
-    launchPdl(backward_quad_kernel<M, CONSTRAINED>, dim3((B + kTile - 1) / kTile), dim3(kQuadWarps * 32), smem, st, model_,
+    launchPdl(backward_quad_kernel<M, CONSTRAINED>, dim3((B + kTile - 1) / kTile), dim3(QuadLayout<M>::W * 32), smem, st, model_,
               ws_, prm_, iter);
   }
 
