@@ -300,3 +300,40 @@ def test_full_size_batches_are_independent_of_the_kernel_variant(gpu, mode):
             assert np.all(cost_rows[accepted, r] < cost_rows[accepted, r - 1])
         assert np.isfinite(big.cost()).all()
         big.close()
+
+
+@pytest.mark.parametrize("env", [{"NMPC_B200_BWD_FUSED": "0"}, {"NMPC_B200_BWD_QUAD": "1"}, {"NMPC_B200_BWD_GS": "4"},
+                                 {"NMPC_B200_FWD_GA": "1"}, {"NMPC_B200_FWD_GA": "16"}])
+def test_every_kernel_variant_agrees_with_the_default(gpu, env, monkeypatch):
+    """The K2 variants (three-kernel pipeline with the TMA tile ring, column-split over 4 warps, in-warp cooperative)
+    and the K3 variants (in-warp fan-out, 16-lane speculation) behind their environment switches against the default
+    (fused K1+K2, phased K3), with and without input limits: bit-identical controls, costs and counters, except the
+    in-warp cooperative K2, whose different product association is held to the M-ref tolerances."""
+    p = O.default_params("cartpole")
+    B, Nh = 200, 100
+    x0, u0 = O.cartpole_x0(B, 21), np.zeros((B, Nh, 1))
+
+    def run(box):
+        s = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+        c = s.config()
+        c.max_iter, c.with_input_constraint = 8, box
+        s.setInputLimitsFunc((np.array([-15.0]), np.array([15.0])))
+        s.solve_batch(0.0, x0, u0)
+        out = (s.controlData().u_list, s.cost(), s.iterations(), s.n_forward(), s.n_backward(), s.status())
+        s.close()
+        return out
+
+    base = [run(False), run(True)]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    exact = "NMPC_B200_BWD_GS" not in env  # the in-warp cooperative K2 associates Fx^T (Vxx Fx): rounding-level differences
+    for want, box in zip(base, (False, True)):
+        got = run(box)
+        if exact:
+            for a, b in zip(got, want):
+                np.testing.assert_array_equal(a, b)
+        else:
+            assert _rel_u(got[0], want[0]).max() <= U_TOL_REF
+            np.testing.assert_allclose(got[1], want[1], rtol=COST_TOL_REF)
+            for a, b in zip(got[2:], want[2:]):
+                np.testing.assert_array_equal(a, b)

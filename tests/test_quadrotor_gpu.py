@@ -99,3 +99,58 @@ def test_quadrotor_fp32_config4(gpu):
     # the optimiser must actually have optimised: cost far below the initial rollout's
     init = solver.trace()[:sub, 0, 1]
     assert np.all(cost[:sub] < init) and np.median(cost[:sub] / init) < 0.5
+
+
+@pytest.mark.parametrize("bwd_gs", ["1", "16"])
+def test_quadrotor_input_limits_boxqp_nu4(gpu, bwd_gs, monkeypatch):
+    """with_input_constraint for n_u = 4 (BoxQP with several free / clamped inputs per step, DDPSolver.hpp:450-497) on
+    both fp64 K2 variants, and the fp32 column-split K2.
+
+    Two DDP iterations: parity at the fp64 tolerance (k to the BoxQP's own 1e-8 termination tolerance).  Beyond that
+    the reference algorithm is discontinuous in its rounding noise: once an input of the trajectory sits ON a limit,
+    the box of the next QP is [lo - u, hi - u] = [+-1e-17, ...] and BoxQP's clamped-set test is an exact
+    `x == lower && grad > 0` (BoxQP.h:189-191), so a last-bit difference in u selects another free set and another
+    step (tools/diag_boxqp_nu4.py shows one: free inputs {0, 1} vs {3}).  With n_u = 1 (cart-pole, config 1) the QP
+    is a clamp and this cannot happen.  Six iterations are therefore gated statistically."""
+    monkeypatch.setenv("NMPC_B200_BWD_GS", bwd_gs)
+    B = 64
+    p = O.default_params("quadrotor")
+    x0, u0 = quadrotor_x0(B, 9), hover_inputs(B)
+    lo = np.array([7.0, -0.05, -0.05, -0.02])
+    hi = np.array([12.0, 0.05, 0.05, 0.02])
+
+    def solve(name, max_iter):
+        s = gpu.DDPSolver(name, params=p, batch_capacity=B)
+        c = s.config()
+        c.horizon_steps, c.max_iter, c.with_input_constraint = N, max_iter, True
+        s.setInputLimitsFunc((lo, hi))
+        s.solve_batch(0.0, x0, u0)
+        return s
+
+    ref2 = O.ddp_solve_batch("quadrotor", p, O.ddp_config(max_iter=2, horizon_steps=N, with_input_constraint=1), x0, u0,
+                             u_lo=lo, u_hi=hi)
+    # the limits bind (forwardPass itself does not clamp, DDPSolver.hpp:548 TODO: the feedback term may leave the box)
+    assert np.any(np.isclose(ref2["u"][:, :, 1], hi[1])) and np.any(np.isclose(ref2["u"][:, :, 0], lo[0]))
+    s = solve("quadrotor_f64", 2)
+    assert np.array_equal(s.iterations(), ref2["iters"]) and np.array_equal(s.status(), ref2["status"])
+    assert np.array_equal(s.n_forward(), ref2["n_fwd"]) and np.array_equal(s.n_backward(), ref2["n_bwd"])
+    u = s.controlData().u_list
+    assert (np.max(np.abs(u - ref2["u"]), axis=(1, 2)) / (1 + np.max(np.abs(ref2["u"]), axis=(1, 2)))).max() <= 1e-8
+    assert np.max(np.abs(s.cost() - ref2["cost"]) / np.abs(ref2["cost"])) <= 1e-10
+    k = s.k_list()
+    assert (np.max(np.abs(k - ref2["k"]), axis=(1, 2)) / (1 + np.max(np.abs(ref2["k"]), axis=(1, 2)))).max() <= 1e-6
+
+    ref6 = O.ddp_solve_batch("quadrotor", p, O.ddp_config(max_iter=6, horizon_steps=N, with_input_constraint=1), x0, u0,
+                             u_lo=lo, u_hi=hi)
+    s = solve("quadrotor_f64", 6)
+    rel_c = np.abs(s.cost() - ref6["cost"]) / np.abs(ref6["cost"])
+    assert np.array_equal(s.iterations(), ref6["iters"]) and np.array_equal(s.status(), ref6["status"])
+    assert np.median(rel_c) <= 1e-2 and rel_c.max() <= 0.1, (np.median(rel_c), rel_c.max())
+    assert np.all(s.cost() < s.trace()[:, 0, 1])  # every instance improved on its initial rollout
+    monkeypatch.delenv("NMPC_B200_BWD_GS")
+
+    s32 = solve("quadrotor", 6)  # fp32, column-split K2 with 12 warps per tile
+    assert np.all(np.isfinite(s32.controlData().u_list)) and np.all(s32.status() >= 0)
+    rel = np.abs(s32.cost() - ref6["cost"]) / np.abs(ref6["cost"])
+    assert np.median(rel) <= 2e-2 and rel.max() <= 0.2, (np.median(rel), rel.max())
+    assert np.all(s32.cost() < s32.trace()[:, 0, 1])
