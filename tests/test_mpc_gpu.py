@@ -217,3 +217,32 @@ def test_trace_dump_files_read_like_the_reference_plot_scripts(gpu, tmp_path):
                                "duration_update")
     assert len(tab) == fm.n_trace()[0]
     np.testing.assert_allclose(tab["kkt_error"], fm.trace()[0, :len(tab), 1], rtol=1e-5)
+
+
+def test_cartpole_swing_up_meets_the_reference_closed_loop_thresholds(gpu):
+    """TestDDPCartPole end to end (TestDDPCartPole.cpp:291-358 with the parameters of tests/test/TestDDPCartPole.test):
+    horizon 2 s / 0.01 s, max_iter 3, limits +-15 N, MPC every 4 ms, plant at 2 ms, 10 s of simulated time = 2500
+    ticks, all on the device.  Instance 0 is the test's own start (hanging down, x = (0, pi, 0, 0)); the others start
+    from perturbed states.  The assertions are the reference's: |pos - ref| < 100 throughout (:336), and at the end
+    |pos - ref| < 1, |theta| < 0.1, |vel| < 1, |omega| < 0.1 (:351-354)."""
+    N, B, ticks = 200, 16, 2500
+    p = O.default_params("cartpole")
+    rng = np.random.default_rng(1)
+    x0 = np.tile([0.0, np.pi, 0.0, 0.0], (B, 1))
+    x0[1:] += rng.uniform(-1, 1, (B - 1, 4)) * [0.5, 0.3, 0.2, 0.2]
+    solver = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+    c = solver.config()
+    c.horizon_steps, c.max_iter, c.with_input_constraint = N, 3, True
+    solver.setInputLimitsFunc((np.array([-15.0]), np.array([15.0])))
+    log = solver.run_mpc(0.0, x0, np.zeros((B, N, 1)), n_ticks=ticks, tick_dt=0.004, plant="sim", shift_inputs=False,
+                         clamp_u0=True, sim_dt=0.002, n_substeps=2)
+    x = log["x"]
+    assert np.all(np.isfinite(x)) and np.all(np.abs(log["u"]) <= 15.0)
+    assert np.all(np.abs(x[:, :, 0]) < 1e2)
+    # theta is not wrapped by the problem: the upright equilibrium reached may be any multiple of 2 pi
+    theta = (x[:, -1, 1] + np.pi) % (2 * np.pi) - np.pi
+    final = np.stack([x[:, -1, 0], theta, x[:, -1, 2], x[:, -1, 3]], axis=1)
+    ok = (np.abs(final[:, 0]) < 1.0) & (np.abs(final[:, 1]) < 1e-1) & (np.abs(final[:, 2]) < 1.0) & (np.abs(final[:, 3]) < 1e-1)
+    assert ok[0], final[0]  # the reference's own scenario
+    assert np.abs(x[0, -1, 1]) < 1e-1  # ... which ends at theta = 0 itself, as the reference asserts
+    assert ok.mean() >= 0.9, final[~ok]
