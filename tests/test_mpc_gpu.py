@@ -246,3 +246,30 @@ def test_cartpole_swing_up_meets_the_reference_closed_loop_thresholds(gpu):
     assert ok[0], final[0]  # the reference's own scenario
     assert np.abs(x[0, -1, 1]) < 1e-1  # ... which ends at theta = 0 itself, as the reference asserts
     assert ok.mean() >= 0.9, final[~ok]
+
+
+def test_fmpc_cartpole_swing_up_meets_the_reference_closed_loop_thresholds(gpu):
+    """TestFmpcCartPole end to end (TestFmpcCartPole.cpp:286-384): horizon 2 s / 0.01 s, max_iter 5, inequality
+    constraints |f| <= 15 N and |pos| <= 20 m inside the problem, MPC every 4 ms, plant at 2 ms with the K_0 feedback
+    term, 10 s = 2500 ticks on the device, Variable.reset(0, 0, 0, 1, 1) at the start.  Same final thresholds as the
+    DDP test (:377-380)."""
+    N, B, ticks = 200, 8, 2500
+    p = O.default_params("fmpc_cartpole")
+    rng = np.random.default_rng(2)
+    x0 = np.tile([0.0, np.pi, 0.0, 0.0], (B, 1))
+    x0[1:] += rng.uniform(-1, 1, (B - 1, 4)) * [0.3, 0.2, 0.1, 0.1]
+    solver = gpu.FmpcSolver("cartpole", params=p, batch_capacity=B)
+    c = solver.config()
+    c.horizon_steps, c.max_iter = N, 5
+    log = solver.run_mpc(0.0, x0, _fmpc_var(solver, B), n_ticks=ticks, tick_dt=0.004, plant="sim", sim_dt=0.002,
+                         n_substeps=2, feedback=True)
+    x = log["x"]
+    assert np.all(np.isfinite(x)) and np.all(np.abs(x[:, :, 0]) < 1e2)
+    assert set(np.unique(log["status"])) <= {1, 5}
+    theta = (x[:, -1, 1] + np.pi) % (2 * np.pi) - np.pi
+    final = np.stack([x[:, -1, 0], theta, x[:, -1, 2], x[:, -1, 3]], axis=1)
+    ok = (np.abs(final[:, 0]) < 1.0) & (np.abs(final[:, 1]) < 1e-1) & (np.abs(final[:, 2]) < 1.0) & (np.abs(final[:, 3]) < 1e-1)
+    assert ok[0], final[0]
+    assert ok.mean() >= 0.75, final[~ok]
+    # the force constraint of the problem holds for the planned input of (almost) every tick once the iterate is feasible
+    assert np.mean(np.abs(log["u"]) <= 15.0 + 1e-6) >= 0.99
