@@ -273,3 +273,39 @@ def test_fmpc_cartpole_swing_up_meets_the_reference_closed_loop_thresholds(gpu):
     assert ok.mean() >= 0.75, final[~ok]
     # the force constraint of the problem holds for the planned input of (almost) every tick once the iterate is feasible
     assert np.mean(np.abs(log["u"]) <= 15.0 + 1e-6) >= 0.99
+
+
+def test_bipedal_full_run_meets_the_reference_thresholds(gpu):
+    """TestDDPBipedal.TestCase1 over its whole 20 s (2000 ticks, horizon 3 s / 0.01 s) on the device: per tick
+    |planned_zmp - ref_zmp| < 1e-2 (TestDDPBipedal.cpp:256), final CoM within 1e-2 of the final reference ZMP and at
+    rest (:271-273).  max_iter is capped at 6 here (the problem is linear-quadratic and converges in 1-3 iterations;
+    the reference leaves the default 500 and stops on its termination tests after as many)."""
+    p = O.default_params("bipedal")
+    N, ticks, dt = 300, 2000, p[0]
+    solver = gpu.DDPSolver("bipedal", params=p, batch_capacity=1)
+    c = solver.config()
+    c.horizon_steps, c.max_iter = N, 6
+    log = solver.run_mpc(0.0, np.zeros((1, 2)), np.zeros((1, N, 1)), n_ticks=ticks, tick_dt=dt, plant="model",
+                         shift_inputs=True)
+    assert np.all(log["status"] == 1), "every tick must converge within the cap"
+    ref = np.array([_ref_zmp(k * dt) for k in range(ticks)])
+    assert np.max(np.abs(log["u"][0, :, 0] - ref)) < 1e-2
+    assert abs(log["x"][0, -1, 0] - _ref_zmp(ticks * dt)) < 1e-2 and abs(log["x"][0, -1, 1]) < 1e-2
+
+
+def test_fmpc_oscillator_full_run_meets_the_reference_thresholds(gpu):
+    """TestFmpcOscillator.SolveMpc over its whole 10 s (2000 ticks of 5 ms, horizon 4 s / 0.01 s, max_iter 3) on the
+    device: status Succeeded or MaxIterationReached and constraints satisfied at every tick (:170, :180), final state
+    within 1e-2 of the origin (:193-194)."""
+    N, ticks, sim_dt = 400, 2000, 0.005
+    p = O.default_params("fmpc_oscillator")
+    solver = gpu.FmpcSolver("oscillator", params=p, batch_capacity=1)
+    c = solver.config()
+    c.horizon_steps, c.max_iter = N, 3
+    log = solver.run_mpc(0.0, np.array([[0.0, 1.0]]), _fmpc_var(solver, 1), n_ticks=ticks, tick_dt=sim_dt, plant="sim",
+                         sim_dt=sim_dt)
+    assert set(np.unique(log["status"])) <= {1, 5}
+    x, u = log["x"][0], log["u"][0, :, 0]
+    g = np.stack([-x[:-1, 1] - 0.05, -u - 1.0, u - 0.9], axis=1)  # ineqConst (TestFmpcOscillator.cpp:68-76)
+    assert np.all(g <= 0), g[np.any(g > 0, axis=1)][:3]
+    assert abs(x[-1, 0]) < 1e-2 and abs(x[-1, 1]) < 1e-2
