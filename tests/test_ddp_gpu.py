@@ -337,3 +337,24 @@ def test_every_kernel_variant_agrees_with_the_default(gpu, env, monkeypatch):
             np.testing.assert_allclose(got[1], want[1], rtol=COST_TOL_REF)
             for a, b in zip(got[2:], want[2:]):
                 np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 7])
+def test_tiny_horizons(gpu, N):
+    """Horizons shorter than the kernels' shared-memory rings (producer / consumer ring of the fused K2, operand rings
+    of K3, chunked K0), unconstrained and BoxQP-constrained, ragged batch."""
+    p = O.default_params("cartpole")
+    B = 5
+    x0, u0 = O.cartpole_x0(B, 40 + N), np.zeros((B, N, 1))
+    for box in (0, 1):
+        ref = O.ddp_solve_batch("cartpole", p, O.ddp_config(horizon_steps=N, max_iter=6, with_input_constraint=box), x0, u0,
+                                u_lo=np.array([-2.0]), u_hi=np.array([2.0]))
+        s = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+        c = s.config()
+        c.horizon_steps, c.max_iter, c.with_input_constraint = N, 6, bool(box)
+        s.setInputLimitsFunc((np.array([-2.0]), np.array([2.0])))
+        s.solve_batch(0.0, x0, u0)
+        assert np.array_equal(s.iterations(), ref["iters"]) and np.array_equal(s.status(), ref["status"])
+        assert _rel_u(s.controlData().u_list, ref["u"]).max() <= U_TOL_REF
+        assert np.max(np.abs(s.cost() - ref["cost"]) / np.abs(ref["cost"])) <= 1e-11
+        s.close()

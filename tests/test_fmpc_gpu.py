@@ -223,3 +223,21 @@ def test_ddp_bipedal_parity_and_receding_horizon(gpu):
         t += p[0]
         x = ro["x"][:, 1, :].copy()
         u = np.concatenate([ro["u"][:, 1:, :], ro["u"][:, -1:, :]], axis=1)
+
+
+@pytest.mark.parametrize("N", [1, 2, 5])
+def test_fmpc_tiny_horizons(gpu, N):
+    """Horizons shorter than the loader-warp rings of F2 / F3."""
+    B = 3
+    x0 = O.cartpole_x0(B, 50 + N) * 0.2
+    p = O.default_params("fmpc_cartpole")
+    solver = gpu.FmpcSolver("cartpole", params=p, batch_capacity=B)
+    c = solver.config()
+    c.horizon_steps, c.max_iter = N, 4
+    var = _initial_variable(solver, B)
+    status = solver.solve_batch(0.0, x0, var)
+    ref = O.fmpc_solve_batch("fmpc_cartpole", p, O.fmpc_config(max_iter=4, horizon_steps=N), x0, _as_dict(var))
+    assert np.array_equal(status, ref["status"])
+    out = _as_dict(solver.variable())
+    for key in ("x", "u", "lambda", "s", "nu"):
+        assert _rel(out[key], ref[key]).max() <= REL_TOL, key
