@@ -68,7 +68,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -309,7 +309,6 @@ def main():
     if rank == 0:
         sampler.start()
     total_ms, _ = timed_loop(device_step, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     iters = solver.iterations()
     n_fwd = solver.n_forward()
     n_bwd = solver.n_backward()
@@ -345,6 +344,8 @@ def main():
     # the result when that event has completed); the L2 flush between steps is outside the events.  The wall clock
     # over the whole loop (flushes included) is reported next to it.
     e2e_ms, e2e_wall = timed_loop(e2e_step, e2e_steps)
+    # the sampler has covered every timed region of this run: `value`, the per-kernel timing solves and `e2e`
+    clocks = sampler.stop() if rank == 0 else None
     h2d = x0_np.nbytes + u0_np.nbytes
     d2h = u0_host_np.nbytes
 
