@@ -1498,7 +1498,8 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
   S * us_ptr = un + bd;
   S * cs_ptr = cn + bd;
 
-  __syncwarp(); // previous users of the ring are done
+  // with GA == 1 every lane copies and reads only its own ring column: no cross-lane hand-over, no warp barriers
+  if constexpr(GA > 1) __syncwarp(); // previous users of the ring are done
 #pragma unroll
   for(int s = 0; s < DEPTH; s++) issue(s, s);
 
@@ -1507,7 +1508,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
   for(int i = 0; i < N; i++)
   {
     cpAsyncWait<DEPTH - 1>(); // this lane's copies of step i have landed
-    __syncwarp(); // ... and so have the other lanes'
+    if constexpr(GA > 1) __syncwarp(); // ... and so have the other lanes'
     S xr[NX], ur[NU], kr[NU], Kr[NU * NX];
     const S * op = ring + (size_t)slot * O::SIZE * IPW + g;
 #pragma unroll
@@ -1518,7 +1519,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutRing(const M & model
     for(int d = 0; d < NU; d++) kr[d] = op[(size_t)(O::KFF + d) * IPW];
 #pragma unroll
     for(int d = 0; d < NU * NX; d++) Kr[d] = op[(size_t)(O::KFB + d) * IPW];
-    __syncwarp(); // everyone has read the slot: refill it with step i + DEPTH
+    if constexpr(GA > 1) __syncwarp(); // everyone has read the slot: refill it with step i + DEPTH
     issue(i + DEPTH, slot);
     slot = (slot + 1 == DEPTH) ? 0 : slot + 1;
 
