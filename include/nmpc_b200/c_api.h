@@ -136,8 +136,12 @@ extern "C"
   int nmpc_b200_ddp_get_config(const nmpc_b200_ddp * h, nmpc_b200_ddp_config * cfg);
 
   /** DDPSolver::setInputLimitsFunc (DDPSolver.h:282-285) for limits constant over the horizon:
-      lower[NU], upper[NU] (host). */
+      lower[NU], upper[NU] (host).  Call after the horizon is configured (the values are replicated per step). */
   int nmpc_b200_ddp_set_input_limits(nmpc_b200_ddp * h, const double * lower, const double * upper);
+  /** DDPSolver::setInputLimitsFunc for limits that CHANGE along the horizon: the values of the reference's
+      input_limits_func_(current_t + i dt) (DDPSolver.hpp:470) for i = 0 .. horizon_steps-1, lower / upper
+      [n_steps][NU] (host).  To be given again before a solve with another current_t or horizon. */
+  int nmpc_b200_ddp_set_input_limits_horizon(nmpc_b200_ddp * h, int n_steps, const double * lower, const double * upper);
 
   /** DDPSolver::solve(current_t, current_x, initial_u_list) (DDPSolver.hpp:27-141) for B <= capacity
       independent instances: x0[B][NX], u_init[B][N][NU].  n_u_steps must equal horizon_steps

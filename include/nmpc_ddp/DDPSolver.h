@@ -174,12 +174,7 @@ public:
                   std::vector<int> * status_out = nullptr)
   {
     ensureHandle();
-    if(config_.with_input_constraint)
-    {
-      if(!input_limits_func_) throw std::runtime_error("[DDP] input limits function is not set.");
-      const auto limits = input_limits_func_(current_t);
-      nmpc_b200::throwOnError(nmpc_b200_ddp_set_input_limits(handle_, limits[0].d, limits[1].d));
-    }
+    if(config_.with_input_constraint) applyInputLimits(current_t);
     nmpc_b200::throwOnError(nmpc_b200_ddp_enable_timing(handle_, 1));
     nmpc_b200::throwOnError(nmpc_b200_ddp_solve(handle_, B, current_t, x0, u_init, n_steps, 0, nullptr));
     last_B_ = B;
@@ -217,12 +212,7 @@ public:
               int * status_log = nullptr)
   {
     ensureHandle();
-    if(config_.with_input_constraint || mpc.clamp_u0)
-    {
-      if(!input_limits_func_) throw std::runtime_error("[DDP] input limits function is not set.");
-      const auto limits = input_limits_func_(current_t);
-      nmpc_b200::throwOnError(nmpc_b200_ddp_set_input_limits(handle_, limits[0].d, limits[1].d));
-    }
+    if(config_.with_input_constraint || mpc.clamp_u0) applyInputLimits(current_t);
     nmpc_b200::throwOnError(nmpc_b200_ddp_run_mpc(handle_, B, current_t, x0, u_init, n_steps, &mpc, x_log, u_log,
                                                   iters_log, status_log, 0, nullptr));
     last_B_ = B;
@@ -267,6 +257,25 @@ public:
   }
 
 protected:
+  /** input_limits_func_(current_t + i dt) for every horizon step, as backwardPass() evaluates it (DDPSolver.hpp:470). */
+  void applyInputLimits(double current_t)
+  {
+    if(!input_limits_func_) throw std::runtime_error("[DDP] input limits function is not set.");
+    const int N = config_.horizon_steps;
+    const int nu = InputDim > 0 ? InputDim : 1;
+    std::vector<double> lo(static_cast<size_t>(N) * nu), hi(static_cast<size_t>(N) * nu);
+    for(int i = 0; i < N; i++)
+    {
+      const auto limits = input_limits_func_(current_t + i * problem_->dt());
+      for(int d = 0; d < InputDim; d++)
+      {
+        lo[static_cast<size_t>(i) * InputDim + d] = limits[0][d];
+        hi[static_cast<size_t>(i) * InputDim + d] = limits[1][d];
+      }
+    }
+    nmpc_b200::throwOnError(nmpc_b200_ddp_set_input_limits_horizon(handle_, N, lo.data(), hi.data()));
+  }
+
   nmpc_b200_ddp_config cConfig() const
   {
     nmpc_b200_ddp_config c;

@@ -86,7 +86,8 @@ EXPORTED_SYMBOLS = [
     "nmpc_b200_last_error", "nmpc_b200_version", "nmpc_b200_device_count", "nmpc_b200_model_dims",
     "nmpc_b200_model_default_params", "nmpc_b200_model_count", "nmpc_b200_model_name", "nmpc_b200_model_eval",
     "nmpc_b200_ddp_config_default", "nmpc_b200_ddp_create", "nmpc_b200_ddp_destroy", "nmpc_b200_ddp_set_config",
-    "nmpc_b200_ddp_get_config", "nmpc_b200_ddp_set_input_limits", "nmpc_b200_ddp_solve", "nmpc_b200_ddp_get",
+    "nmpc_b200_ddp_get_config", "nmpc_b200_ddp_set_input_limits", "nmpc_b200_ddp_set_input_limits_horizon",
+    "nmpc_b200_ddp_solve", "nmpc_b200_ddp_get",
     "nmpc_b200_ddp_sync", "nmpc_b200_ddp_enable_timing", "nmpc_b200_ddp_get_durations", "nmpc_b200_ddp_run_mpc",
     "nmpc_b200_fmpc_config_default", "nmpc_b200_fmpc_create", "nmpc_b200_fmpc_destroy", "nmpc_b200_fmpc_set_config",
     "nmpc_b200_fmpc_solve", "nmpc_b200_fmpc_get", "nmpc_b200_fmpc_sync", "nmpc_b200_fmpc_enable_timing",
@@ -123,6 +124,7 @@ def lib():
         L.nmpc_b200_ddp_set_config.argtypes = [C.c_void_p, C.c_void_p]
         L.nmpc_b200_ddp_get_config.argtypes = [C.c_void_p, C.c_void_p]
         L.nmpc_b200_ddp_set_input_limits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nmpc_b200_ddp_set_input_limits_horizon.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.nmpc_b200_ddp_sync.argtypes = [C.c_void_p]
         L.nmpc_b200_ddp_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.nmpc_b200_ddp_get_durations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

@@ -88,8 +88,6 @@ public:
     NMPC_CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     NMPC_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&h_counter_), sizeof(int)));
     Bp_ = ((capacity_ + 127) / 128) * 128;
-    u_lo_.assign(NU, 0.0);
-    u_hi_.assign(NU, 0.0);
     NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)backwardSmemBytes(maxThreadsPerBlock())));
     NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -119,17 +117,44 @@ public:
 
   void setInputLimits(const double * lower, const double * upper) override
   {
+    // limits constant over the horizon: the same pair at every step
+    const int N = cfg_.horizon_steps;
+    std::vector<double> lo((size_t)N * NU), hi((size_t)N * NU);
+    for(int i = 0; i < N; i++)
+      for(int d = 0; d < NU; d++)
+      {
+        lo[(size_t)i * NU + d] = lower[d];
+        hi[(size_t)i * NU + d] = upper[d];
+      }
+    setInputLimitsHorizon(N, lo.data(), hi.data());
+    limits_vary_ = false;
+  }
+
+  /** input_limits_func_(current_t + i dt) for i = 0 .. N-1 (DDPSolver.h:282-285, DDPSolver.hpp:470): lower / upper
+      [n_steps][NU]. */
+  void setInputLimitsHorizon(int n_steps, const double * lower, const double * upper) override
+  {
     DeviceGuard guard(device_);
-    std::vector<S> lo(NU), hi(NU);
-    for(int d = 0; d < NU; d++)
+    const int N = cfg_.horizon_steps;
+    if(n_steps != N)
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "input limits are needed for " + std::to_string(N) + " steps but "
+                                                      + std::to_string(n_steps) + " were given");
+    if(lower == nullptr || upper == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null input limits");
+    u_lo_.assign(lower, lower + (size_t)N * NU);
+    u_hi_.assign(upper, upper + (size_t)N * NU);
+    std::vector<S> lo((size_t)N * NU), hi((size_t)N * NU);
+    limits_vary_ = false;
+    for(size_t e = 0; e < lo.size(); e++)
     {
-      u_lo_[d] = lower[d];
-      u_hi_[d] = upper[d];
-      lo[d] = S(lower[d]);
-      hi[d] = S(upper[d]);
+      lo[e] = S(lower[e]);
+      hi[e] = S(upper[e]);
+      if(lower[e] != lower[e % NU] || upper[e] != upper[e % NU]) limits_vary_ = true;
     }
-    NMPC_CUDA_CHECK(cudaMemcpy(d_u_lo_.ptr, lo.data(), sizeof(S) * NU, cudaMemcpyHostToDevice));
-    NMPC_CUDA_CHECK(cudaMemcpy(d_u_hi_.ptr, hi.data(), sizeof(S) * NU, cudaMemcpyHostToDevice));
+    if(NU > 0)
+    {
+      NMPC_CUDA_CHECK(cudaMemcpy(d_u_lo_.ptr, lo.data(), sizeof(S) * lo.size(), cudaMemcpyHostToDevice));
+      NMPC_CUDA_CHECK(cudaMemcpy(d_u_hi_.ptr, hi.data(), sizeof(S) * hi.size(), cudaMemcpyHostToDevice));
+    }
     have_limits_ = true;
   }
 
@@ -165,6 +190,10 @@ public:
       throw Error(NMPC_B200_ERR_UNSUPPORTED, "plant = 1 needs a functor with stateEq(t, x, u, dt)");
     if(mpc.plant == 1 && mpc.n_substeps <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "n_substeps must be positive");
     if(mpc.clamp_u0 && !have_limits_) throw Error(NMPC_B200_ERR_RUNTIME, "clamp_u0 is set but no input limits were given");
+    if(limits_vary_ && (mpc.clamp_u0 || cfg_.with_input_constraint))
+      throw Error(NMPC_B200_ERR_UNSUPPORTED,
+                  "the device-resident MPC loop needs input limits that are constant over time (the limits of a "
+                  "horizon are given per step index, and the loop shifts the horizon every tick)");
     cudaStream_t st = beginSolve(B, n_u_steps, x0, u_init, stream);
     const size_t T = mpc.n_ticks;
     const size_t Bp = Bp_;
@@ -830,8 +859,8 @@ protected:
     trace_.allocate((size_t)(cfg_.max_iter + 1) * kTraceFields * Bp);
     scal_.allocate(5 * Bp);
     ints_.allocate(5 * Bp);
-    d_u_lo_.allocate(NU > 0 ? NU : 1);
-    d_u_hi_.allocate(NU > 0 ? NU : 1);
+    d_u_lo_.allocate(NU > 0 ? N * NU : 1);
+    d_u_hi_.allocate(NU > 0 ? N * NU : 1);
     d_counter_.allocate(1);
     d_fan_count_.allocate(1);
     NMPC_CUDA_CHECK(cudaMemset(d_fan_count_.ptr, 0, sizeof(int)));
@@ -860,7 +889,17 @@ protected:
     ws_.iters = ints_.ptr + 2 * Bp;
     ws_.n_fwd = ints_.ptr + 3 * Bp;
     ws_.n_bwd = ints_.ptr + 4 * Bp;
-    if(have_limits_) setInputLimits(u_lo_.data(), u_hi_.data());
+    if(have_limits_)
+    {
+      // a changed horizon keeps constant limits; step-wise limits have to be given again for the new horizon
+      if(limits_vary_ || u_lo_.size() < (size_t)NU)
+        have_limits_ = false;
+      else
+      {
+        const std::vector<double> lo(u_lo_.begin(), u_lo_.begin() + NU), hi(u_hi_.begin(), u_hi_.begin() + NU);
+        setInputLimits(lo.data(), hi.data());
+      }
+    }
     B_ = 0;
   }
 
@@ -883,6 +922,7 @@ protected:
   int * h_counter_ = nullptr;
   std::vector<double> u_lo_, u_hi_;
   bool have_limits_ = false;
+  bool limits_vary_ = false; //!< the limits differ between horizon steps
   bool timing_ = false;
   std::vector<cudaEvent_t> events_;
   int n_events_used_ = 0;

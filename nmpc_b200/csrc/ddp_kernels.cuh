@@ -78,7 +78,7 @@ struct Workspace
   S * dlambda;
   S * cost_sum;
   S * dV;
-  S * u_lo; //!< [NU] input limits (with_input_constraint)
+  S * u_lo; //!< [N][NU] input limits of every horizon step (with_input_constraint; input_limits_func_(t_i))
   S * u_hi;
   int * status;
   int * sel;
@@ -802,8 +802,8 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
       for(int a = 0; a < NU; a++)
       {
         const S uv = u_cur[a];
-        lo[a] = ws.u_lo[a] - uv;
-        hi[a] = ws.u_hi[a] - uv;
+        lo[a] = ws.u_lo[(size_t)i * NU + a] - uv; // input_limits_func_(t_i) (:470)
+        hi[a] = ws.u_hi[(size_t)i * NU + a] - uv;
         init[a] = warmStartFromNextStep<M>(model, prm.t0, i, N) ? k_prev[a] : S(0);
       }
       BoxQPResult<S, NU> qp;

@@ -26,6 +26,7 @@ public:
   virtual void setConfig(const nmpc_b200_ddp_config & cfg) = 0;
   virtual const nmpc_b200_ddp_config & config() const = 0;
   virtual void setInputLimits(const double * lower, const double * upper) = 0;
+  virtual void setInputLimitsHorizon(int n_steps, const double * lower, const double * upper) = 0;
   virtual void solve(int B,
                      double current_t,
                      const double * x0,

@@ -108,6 +108,7 @@ class DDPSolver:
         self._applied = None
         self._B = 0
         self._timing = False
+        self._limits_func = None
         s = self._config.to_struct()
         check(lib().nmpc_b200_ddp_create(problem.encode(), self.params.ctypes.data_as(C.c_void_p),
                                          int(self.params.size), C.byref(s), self.batch_capacity, int(device),
@@ -120,14 +121,32 @@ class DDPSolver:
         return self._config
 
     def setInputLimitsFunc(self, input_limits):
-        """``input_limits``: (lower, upper) arrays of length NU, or a callable t -> (lower, upper) that is
-        constant over the horizon (evaluated at t = 0)."""
+        """DDPSolver::setInputLimitsFunc (DDPSolver.h:282-285).  ``input_limits``: a callable t -> (lower, upper), each of
+        length NU, evaluated at every horizon time ``current_t + i * dt`` of each solve like the reference's
+        input_limits_func_ (DDPSolver.hpp:470); or a constant (lower, upper) pair."""
         if callable(input_limits):
-            input_limits = input_limits(0.0)
+            self._limits_func = input_limits
+            return
+        self._limits_func = None
+        self._apply_config()
         lo = np.ascontiguousarray(input_limits[0], dtype=np.float64).reshape(self.nu)
         hi = np.ascontiguousarray(input_limits[1], dtype=np.float64).reshape(self.nu)
         check(lib().nmpc_b200_ddp_set_input_limits(self._h, lo.ctypes.data_as(C.c_void_p),
                                                    hi.ctypes.data_as(C.c_void_p)))
+
+    def _apply_limits(self, current_t):
+        """Evaluate a limits callable over the horizon of the coming solve."""
+        func = getattr(self, "_limits_func", None)
+        if func is None:
+            return
+        N = self._config.horizon_steps
+        dt = float(self.params[0])  # every functor of this library keeps dt first in its flat parameter vector
+        lo, hi = np.empty((N, self.nu)), np.empty((N, self.nu))
+        for i in range(N):
+            l, h = func(current_t + i * dt)
+            lo[i], hi[i] = np.asarray(l, dtype=np.float64).reshape(self.nu), np.asarray(h, dtype=np.float64).reshape(self.nu)
+        check(lib().nmpc_b200_ddp_set_input_limits_horizon(self._h, N, lo.ctypes.data_as(C.c_void_p),
+                                                           hi.ctypes.data_as(C.c_void_p)))
 
     def solve(self, current_t, current_x, initial_u_list):
         """Single-instance ``solve`` (DDPSolver.hpp:27-141); returns True iff converged (retval == 1)."""
@@ -141,6 +160,7 @@ class DDPSolver:
         """Solve B independent instances.  x0: [B, NX]; u_init: [B, n_steps, NU] (numpy, or float64 torch
         CUDA tensors for a device-resident call).  Returns the per-instance ``solve()`` return values."""
         self._apply_config()
+        self._apply_limits(float(current_t))
         x_shape = tuple(x0.shape)
         if len(x_shape) != 2 or x_shape[1] != self.nx:
             raise InvalidArgument(_capi.ERR_INVALID_ARGUMENT, f"x0 must be [B, {self.nx}], got {x_shape}")
@@ -171,6 +191,7 @@ class DDPSolver:
         ``shift_inputs=False, clamp_u0=True`` (TestDDPCartPole.cpp:330, :388-396).
         Returns a dict: x [B, n_ticks+1, NX], u [B, n_ticks, NU] (applied inputs), iters, status [B, n_ticks]."""
         self._apply_config()
+        self._apply_limits(float(current_t))
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         u_init = np.ascontiguousarray(u_init, dtype=np.float64)
         B = x0.shape[0]

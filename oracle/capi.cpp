@@ -7,6 +7,7 @@
 //   K[B][N][NU*NX] (column-major NU x NX per step), trace[B][max_iter+1][9].
 #include <cstring>
 #include <memory>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -79,7 +80,9 @@ int ddpSolveBatch(const double * params,
                   int * iters_out,
                   int * n_fwd_out,
                   int * n_bwd_out,
-                  int nthreads)
+                  int nthreads,
+                  const double * u_lo_steps = nullptr, // [N][NU]: limits that change along the horizon
+                  const double * u_hi_steps = nullptr)
 {
   const int N = cfg->horizon_steps;
   const int TR = cfg->max_iter + 1;
@@ -117,7 +120,26 @@ int ddpSolveBatch(const double * params,
         lim[0][d] = u_lo[d];
         lim[1][d] = u_hi[d];
       }
-      solver.setInputLimitsFunc([lim](double) { return lim; });
+      if(u_lo_steps != nullptr && u_hi_steps != nullptr)
+      {
+        // input_limits_func_(t) of the reference is a function of time: here a table over the horizon steps
+        const double dt = problem->dt();
+        solver.setInputLimitsFunc([=](double t) {
+          long i = std::lround((t - t0) / dt);
+          i = i < 0 ? 0 : (i > N - 1 ? N - 1 : i);
+          std::array<Vec<NU>, 2> l;
+          for(int d = 0; d < NU; d++)
+          {
+            l[0][d] = u_lo_steps[(size_t)i * NU + d];
+            l[1][d] = u_hi_steps[(size_t)i * NU + d];
+          }
+          return l;
+        });
+      }
+      else
+      {
+        solver.setInputLimitsFunc([lim](double) { return lim; });
+      }
     }
 
     std::vector<Vec<NU>> u_list(N);
@@ -372,6 +394,29 @@ int oracle_ddp_solve_batch(const char * model,
                                                          cost_out, k_out, K_out, trace_out, n_trace_out, status_out,
                                                          iters_out, n_fwd_out, n_bwd_out, nthreads);
   return -2;
+}
+
+/** oracle_ddp_solve_batch for the cart-pole with input limits that change along the horizon (u_lo_steps /
+    u_hi_steps [N][1]): the reference's input_limits_func_(t) evaluated at t_i (DDPSolver.hpp:470). */
+int oracle_ddp_solve_batch_cartpole_tv(const double * params,
+                                       const oracle_ddp_config * cfg,
+                                       int B,
+                                       double t0,
+                                       const double * x0,
+                                       const double * u_init,
+                                       const double * u_lo_steps,
+                                       const double * u_hi_steps,
+                                       double * x_out,
+                                       double * u_out,
+                                       double * cost_out,
+                                       int * status_out,
+                                       int * iters_out,
+                                       int nthreads)
+{
+  const double zero = 0.0;
+  return ddpSolveBatch<DDPProblemCartPole, 4, 1>(params, cfg, B, t0, x0, u_init, &zero, &zero, x_out, u_out, cost_out,
+                                                 nullptr, nullptr, nullptr, nullptr, status_out, iters_out, nullptr,
+                                                 nullptr, nthreads, u_lo_steps, u_hi_steps);
 }
 
 int oracle_model_eval(const char * model,

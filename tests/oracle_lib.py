@@ -234,3 +234,22 @@ def cartpole_x0(B, seed):
     x0[:, 2] = rng.uniform(-1.0, 1.0, B)
     x0[:, 3] = rng.uniform(-1.0, 1.0, B)
     return x0
+
+
+def ddp_solve_cartpole_tv_limits(params, cfg, x0, u_init, u_lo_steps, u_hi_steps, t0=0.0):
+    """Cart-pole DDP with input limits that change along the horizon: u_lo_steps / u_hi_steps [N, 1]."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, 4)
+    B, N = x0.shape[0], cfg.horizon_steps
+    u_init = np.ascontiguousarray(u_init, dtype=np.float64).reshape(B, N, 1)
+    lo = np.ascontiguousarray(u_lo_steps, dtype=np.float64).reshape(N, 1)
+    hi = np.ascontiguousarray(u_hi_steps, dtype=np.float64).reshape(N, 1)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    out = {"x": np.zeros((B, N + 1, 4)), "u": np.zeros((B, N, 1)), "cost_list": np.zeros((B, N + 1)),
+           "status": np.zeros(B, dtype=np.int32), "iters": np.zeros(B, dtype=np.int32)}
+    rc = lib().oracle_ddp_solve_batch_cartpole_tv(_p(params), C.byref(cfg), C.c_int(B), C.c_double(t0), _p(x0), _p(u_init),
+                                                  _p(lo), _p(hi), _p(out["x"]), _p(out["u"]), _p(out["cost_list"]),
+                                                  _p(out["status"]), _p(out["iters"]), C.c_int(0))
+    if rc != 0:
+        raise RuntimeError(f"oracle_ddp_solve_batch_cartpole_tv failed: {rc}")
+    out["cost"] = out["cost_list"].sum(axis=1)
+    return out

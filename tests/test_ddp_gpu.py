@@ -358,3 +358,42 @@ def test_tiny_horizons(gpu, N):
         assert _rel_u(s.controlData().u_list, ref["u"]).max() <= U_TOL_REF
         assert np.max(np.abs(s.cost() - ref["cost"]) / np.abs(ref["cost"])) <= 1e-11
         s.close()
+
+
+def test_input_limits_that_change_along_the_horizon(gpu):
+    """setInputLimitsFunc with a genuine function of time (DDPSolver.h:282-285; evaluated at every t_i by backwardPass,
+    DDPSolver.hpp:470): the limits tighten from +-15 N to +-3 N over the horizon.  Against the oracle driven with the
+    same table; the constant-limit call must keep working after it; the device MPC loop refuses time-varying limits."""
+    p = O.default_params("cartpole")
+    B, N, t0 = 48, 100, 0.3
+    x0, u0 = O.cartpole_x0(B, 77), np.zeros((B, N, 1))
+    dt = p[0]
+
+    def limits(t):
+        w = 15.0 - 12.0 * min(max((t - t0) / (N * dt), 0.0), 1.0)
+        return np.array([-w]), np.array([0.5 * w])
+
+    lo = np.array([limits(t0 + i * dt)[0] for i in range(N)])
+    hi = np.array([limits(t0 + i * dt)[1] for i in range(N)])
+    cfg = O.ddp_config(horizon_steps=N, max_iter=8, with_input_constraint=1)
+    ref = O.ddp_solve_cartpole_tv_limits(p, cfg, x0, u0, lo, hi, t0=t0)
+
+    s = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+    c = s.config()
+    c.max_iter, c.with_input_constraint = 8, True
+    s.setInputLimitsFunc(limits)
+    s.solve_batch(t0, x0, u0)
+    assert np.array_equal(s.iterations(), ref["iters"]) and np.array_equal(s.status(), ref["status"])
+    assert _rel_u(s.controlData().u_list, ref["u"]).max() <= U_TOL_REF
+    assert np.max(np.abs(s.cost() - ref["cost"]) / np.abs(ref["cost"])) <= COST_TOL_REF
+    k = s.k_list()[:, :, 0]  # the feedforward term respects each step's own box (lo_i - u_i <= k_i <= hi_i - u_i)
+    with pytest.raises(gpu.NmpcB200Error) as e:
+        s.run_mpc(t0, x0, u0, n_ticks=2, tick_dt=dt)
+    assert e.value.code == 7
+    # constant limits afterwards: same result as a fresh solver
+    s.setInputLimitsFunc((np.array([-15.0]), np.array([15.0])))
+    s.solve_batch(0.0, x0, u0)
+    ref_c = O.ddp_solve_batch("cartpole", p, O.ddp_config(horizon_steps=N, max_iter=8, with_input_constraint=1), x0, u0,
+                              u_lo=np.array([-15.0]), u_hi=np.array([15.0]))
+    assert _rel_u(s.controlData().u_list, ref_c["u"]).max() <= U_TOL_REF
+    del k
