@@ -500,7 +500,7 @@ protected:
     const dim3 grid1((B + tpb1 - 1) / tpb1, N + 1);
     iter_event_base_ = n_events_used_;
     iters_launched_ = 0;
-    const bool fused = backwardUsesFused(B); // Step 1 then happens inside the backward kernel
+    const bool fused = use_fused_; // Step 1 then happens inside the backward kernel
     for(int iter = 1; iter <= cfg_.max_iter; iter++)
     {
       if(!fused) launchPdl(linearize_kernel<M>, grid1, dim3(tpb1), 0, st, model_, ws_, prm_);
@@ -659,7 +659,7 @@ protected:
   {
     if constexpr(NX < 8)
     {
-      if(backwardUsesFused(B))
+      if(use_fused_)
       {
         if(cfg_.with_input_constraint)
           launchBackwardFused<true>(B, iter, st);
@@ -852,8 +852,19 @@ protected:
       ws_.u[s] = u_[s].ptr;
       ws_.cost[s] = cost_[s].ptr;
     }
-    deriv_.allocate(N * L::SIZE * Bp);
-    vterm_.allocate((size_t)(NX + NX * NX) * Bp);
+    // the K1 -> K2 derivative tiles and terminal derivatives exist only in the three-kernel pipeline (4.8 GB at
+    // B = 131072 for cart-pole); the fused K1+K2 keeps them in shared memory.  The variant is fixed per engine.
+    use_fused_ = backwardUsesFused(capacity_);
+    if(use_fused_)
+    {
+      deriv_.release();
+      vterm_.release();
+    }
+    else
+    {
+      deriv_.allocate(N * L::SIZE * Bp);
+      vterm_.allocate((size_t)(NX + NX * NX) * Bp);
+    }
     kff_.allocate(N * NU * Bp);
     kfb_.allocate(N * NU * NX * Bp);
     trace_.allocate((size_t)(cfg_.max_iter + 1) * kTraceFields * Bp);
@@ -922,6 +933,7 @@ protected:
   int * h_counter_ = nullptr;
   std::vector<double> u_lo_, u_hi_;
   bool have_limits_ = false;
+  bool use_fused_ = false; //!< K1 fused into K2 (decided once, at allocation)
   bool limits_vary_ = false; //!< the limits differ between horizon steps
   bool timing_ = false;
   std::vector<cudaEvent_t> events_;
