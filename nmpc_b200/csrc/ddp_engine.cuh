@@ -577,7 +577,7 @@ protected:
     constexpr int kWarps = 2;
     const int grid = (B + kWarps * C::IPW - 1) / (kWarps * C::IPW);
     const size_t smem = sizeof(S) * (size_t)kWarps * C::WARP_ELEMS;
-    static bool attr_set = false;
+    bool & attr_set = attr_set_[0 + (CONSTRAINED ? 1 : 0)]; // per engine: function attributes are per device
     if(!attr_set)
     {
       cudaFuncSetAttribute(backward_coop_kernel<M, kCoopGS, CONSTRAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -613,7 +613,7 @@ protected:
   void launchBackwardFused(int B, int iter, cudaStream_t st)
   {
     const size_t smem = FusedLayout<M>::bytes();
-    static bool attr_set = false;
+    bool & attr_set = attr_set_[2 + (CONSTRAINED ? 1 : 0)]; // per engine: function attributes are per device
     if(!attr_set)
     {
       NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_fused_kernel<M, CONSTRAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -644,7 +644,7 @@ protected:
   void launchBackwardQuad(int B, int iter, cudaStream_t st)
   {
     const size_t smem = QuadLayout<M>::bytes();
-    static bool attr_set = false;
+    bool & attr_set = attr_set_[4 + (CONSTRAINED ? 1 : 0)]; // per engine: function attributes are per device
     if(!attr_set)
     {
       NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_quad_kernel<M, CONSTRAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -700,7 +700,7 @@ protected:
     constexpr int ipw = 32 / GA;
     const int grid = (B + kWarps * ipw - 1) / (kWarps * ipw);
     const size_t smem = sizeof(S) * (size_t)kWarps * 4 * FwdOperands<NX, NU>::SIZE * ipw;
-    static bool attr_set = false;
+    bool & attr_set = attr_set_[6 + (GA == 16 ? 1 : 0)]; // per engine: function attributes are per device
     if(!attr_set)
     {
       cudaFuncSetAttribute(forward_spec_kernel<M, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -717,7 +717,7 @@ protected:
     {
       constexpr int kWarps = 1; // one warp per CTA spreads 4096 instances over 128 SMs
       const size_t smem = sizeof(S) * (size_t)kWarps * 4 * O::SIZE * 32;
-      static bool attr_set = false;
+      bool & attr_set = attr_set_[8]; // per engine: function attributes are per device
       if(!attr_set)
       {
         cudaFuncSetAttribute(forward_first_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -933,6 +933,7 @@ protected:
   int * h_counter_ = nullptr;
   std::vector<double> u_lo_, u_hi_;
   bool have_limits_ = false;
+  bool attr_set_[9] = {false, false, false, false, false, false, false, false, false};
   bool use_fused_ = false; //!< K1 fused into K2 (decided once, at allocation)
   bool limits_vary_ = false; //!< the limits differ between horizon steps
   bool timing_ = false;

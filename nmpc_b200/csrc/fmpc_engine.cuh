@@ -380,7 +380,7 @@ protected:
     using R3 = ForwardRows<NX, NU, NG>;
     const int tpb2 = 64, tpb3 = 64, grid2 = (B + kTile - 1) / kTile, grid3 = grid2;
     const size_t smem2 = R2::bytes(sizeof(S)), smem3 = R3::bytes(sizeof(S));
-    static bool attr_set = false;
+    bool & attr_set = attr_set_[0]; // per engine: function attributes are per device
     if(!attr_set)
     {
       NMPC_CUDA_CHECK(cudaFuncSetAttribute(fmpc_backward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -538,6 +538,7 @@ protected:
   DeviceBuffer<double> stage_in_, stage_out_;
   int * h_flag_ = nullptr;
   bool timing_ = false;
+  bool attr_set_[2] = {false, false};
   std::vector<cudaEvent_t> events_;
   int n_events_used_ = 0;
   int iter_event_base_ = 0;

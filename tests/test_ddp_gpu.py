@@ -397,3 +397,28 @@ def test_input_limits_that_change_along_the_horizon(gpu):
                               u_lo=np.array([-15.0]), u_hi=np.array([15.0]))
     assert _rel_u(s.controlData().u_list, ref_c["u"]).max() <= U_TOL_REF
     del k
+
+
+def test_two_devices_in_one_process(gpu):
+    """Handles on different devices are independent (c_api.h): the kernels that need more than 48 KB of dynamic shared
+    memory (FMPC sweeps, column-split K2) must have their function attribute set on EVERY device.  Skipped on a
+    single-GPU box."""
+    if gpu.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from test_quadrotor_gpu import N as NQ, hover_inputs, quadrotor_x0
+
+    x0 = O.cartpole_x0(64, 1)
+    outs = []
+    for dev in (0, 1):
+        s = gpu.FmpcSolver("cartpole", batch_capacity=64, device=dev)
+        s.config().max_iter = 3
+        v = s.make_variable(64)
+        v.reset(0.0, 0.0, 0.0, 1.0, 1.0)
+        s.solve_batch(0.0, x0, v)
+        outs.append(s.variable().u_list.copy())
+        q = gpu.DDPSolver("quadrotor", batch_capacity=64, device=dev)
+        q.config().horizon_steps, q.config().max_iter = NQ, 2
+        q.solve_batch(0.0, quadrotor_x0(64, 1), hover_inputs(64))
+        outs.append(q.cost().copy())
+    np.testing.assert_array_equal(outs[0], outs[2])
+    np.testing.assert_array_equal(outs[1], outs[3])
