@@ -56,8 +56,8 @@ def quadrotor():
     return out
 
 
-def fmpc():
-    B, N = 1024, 100
+def fmpc(B=1024):
+    N = 100
     x0 = O.cartpole_x0(B, 3)
     s = nmpc_b200.FmpcSolver("cartpole", batch_capacity=B)
     s.config().horizon_steps = N
@@ -79,6 +79,8 @@ if __name__ == "__main__":
         res.update(quadrotor())
     if what in ("fmpc", "all"):
         res.update(fmpc())
+    if what == "fmpc_sweep":
+        res["fmpc_sweep"] = [fmpc(B)["fmpc_cartpole"] for B in (1024, 4096, 16384, 65536)]
     print(json.dumps(res))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "time_configs.json"), "a") as f:
