@@ -5,8 +5,8 @@
  * along one warp's instruction stream, and a 4096-instance batch offers only 128 such warps to 592 warp
  * schedulers (ncu: 1500 cycles per horizon step, fp64 pipe of the one busy scheduler 55 % busy, the other three
  * schedulers of the SM idle).  Here lane l of EVERY warp of the CTA works on instance tile*32 + l, and warp w owns
- * columns w, w+4, ... of the n_x x n_x matrices (Vxx, Tx = Fx^T Vxx, Qxx, Vxx') plus the matching columns of
- * Tu = Fu^T Vxx, Qux, K.  The four warps run on the four schedulers of the SM, each with its own fp64 pipe, and
+ * columns w, w+W, ... of the n_x x n_x matrices (Vxx, Tx = Fx^T Vxx, Qxx, Vxx') plus the matching columns of
+ * Tu = Fu^T Vxx, Qux, K.  The warps are spread over the four schedulers of the SM, each with its own fp64 pipe, and
  * exchange columns through shared memory at three block barriers per step (measured: 36 cycles per
  * STS / bar.sync / LDS round, tools/fp64_latency.cu):
  *
@@ -19,7 +19,7 @@
  *
  * Every scalar is computed by exactly the expression of ddp::backwardSweep (same operands, same order), so the
  * two variants agree bit for bit.  The step's derivative tile arrives by one bulk (TMA) copy per step into a
- * two-stage ring shared by the four warps; the wait on its mbarrier is issued one phase early so that its
+ * two-stage ring shared by the W warps; the wait on its mbarrier is issued one phase early so that its
  * latency overlaps phase C of the previous step.
  *
  * Reference: DDPSolver.hpp:188-231 (Step 2), :343-534 (backwardPass).
@@ -81,7 +81,7 @@ __device__ __forceinline__ int mbarTryWait(unsigned long long * bar, unsigned pa
 }
 
 /** One column-split backwardPass() sweep.  All 128 threads execute every barrier; only lanes with `work` (and no
-    factorisation failure so far) compute.  The return value is identical in the four warps of a lane. */
+    factorisation failure so far) compute.  The return value is identical in all warps of a lane. */
 template<class M, bool CONSTRAINED>
 __device__ __forceinline__ bool backwardSweepQuad(const M & model,
                                                   const Workspace<typename M::Scalar> & ws,
@@ -593,7 +593,7 @@ __device__ __forceinline__ bool backwardSweepQuad(const M & model,
   return ok;
 }
 
-/** procOnce() Step 2 (DDPSolver.hpp:188-231), four warps per 32-instance tile. */
+/** procOnce() Step 2 (DDPSolver.hpp:188-231), W warps per 32-instance tile. */
 template<class M, bool CONSTRAINED>
 __global__ void __launch_bounds__(QuadLayout<M>::W * 32) backward_quad_kernel(const __grid_constant__ M model,
                                                                         const __grid_constant__ Workspace<typename M::Scalar> ws,
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(QuadLayout<M>::W * 32) backward_quad_kernel(co
   S dV0 = S(0), dV1 = S(0), k_rel_norm = S(0);
   bool need = live;
   bool failed = false;
-  // `need` of a lane is the same in the four warps, so the trip count is uniform over the CTA
+  // `need` of a lane is the same in all warps, so the trip count is uniform over the CTA
   while(__syncthreads_or(need))
   {
     if(need) n_bwd++;

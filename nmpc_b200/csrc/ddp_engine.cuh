@@ -1,9 +1,10 @@
 /* nmpc_b200 -- host side of the batched DDP engine for one functor type M.
  *
  * Owns the device workspace for `capacity` instances, converts the instance-major arrays of the
- * C ABI to the batch-innermost device layout, and enqueues K0, then max_iter x {K1, K2, K3} on one
- * stream with no host round trip (per-instance lambda/status/iteration counters live on the device;
- * finished instances' threads return immediately).  For max_iter > kCheckStride the host polls an
+ * C ABI to the batch-innermost device layout, and enqueues K0, then max_iter x {K1, K2, K3} -- for n_x < 8
+ * max_iter x {K1+K2 fused, K3} -- on one stream with no host round trip (per-instance lambda/status/iteration
+ * counters live on the device; finished instances' threads return immediately).  Kernel variants are chosen here by
+ * n_x and batch size (thresholds measured on B200); runMpc() chains whole solves tick after tick.  For max_iter > kCheckStride the host polls an
  * active-instance counter every kCheckStride iterations so that a batch that has converged does not
  * pay for hundreds of empty launches (DDPSolver::Configuration::max_iter defaults to 500).
  */

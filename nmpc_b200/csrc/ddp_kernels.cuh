@@ -10,13 +10,16 @@
  *   K1 linearize_kernel      procOnce() Step 1, parallel over (instance, step) :157-185
  *   K2 backward_kernel       procOnce() Step 2 + backwardPass() + termination  :188-231, :343-534
  *   K3 forward_kernel        procOnce() Step 3/4 + forwardPass()               :234-339, :537-560
+ * Variants in their own headers: ddp_backward_fused.cuh (K1 + K2 in one kernel, the default for n_x < 8),
+ * ddp_backward_quad.cuh / ddp_backward_coop.cuh (column-split K2 for n_x >= 8), ddp_forward_phased.cuh (K3 for
+ * latency-bound batches), ddp_mpc.cuh (tick-to-tick kernel of the MPC loop).
  *
  * Device layout (S = scalar type, Bp = padded batch):
  *   x[2]    [N+1][NX][Bp]   current / candidate trajectories; sel[b] says which one is current
  *   u[2]    [N][NU][Bp]
  *   cost[2] [N+1][Bp]
- *   deriv   [N][BLK][Bp]    BLK = {Fx, Fu, Lx, Lu, Lxx, Luu, Lxu} column-major, in that order
- *   vterm   [NX+NX*NX][Bp]  terminal Vx, Vxx
+ *   deriv   [N][tile][BLK][32]  BLK = {Fx, Fu, Lx, Lu, Lxx, Luu, Lxu} column-major; three-kernel pipeline only
+ *   vterm   [NX+NX*NX][Bp]  terminal Vx, Vxx; three-kernel pipeline only
  *   kff     [N][NU][Bp], kfb [N][NU*NX][Bp]
  *   trace   [max_iter+1][9][Bp]
  *   per-instance scalars: lambda, dlambda, cost_sum, dV[2], status, sel, iters, n_fwd, n_bwd
