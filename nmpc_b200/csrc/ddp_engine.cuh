@@ -716,16 +716,15 @@ protected:
     using O = FwdOperands<NX, NU>;
     ensureFanout();
     {
-      constexpr int kWarps = 1; // one warp per CTA spreads 4096 instances over 128 SMs
-      const size_t smem = sizeof(S) * (size_t)kWarps * 4 * O::SIZE * 32;
+      // one 32-instance tile per CTA (compute warp + loader warp): 4096 instances cover 128 SMs
+      const size_t smem = sizeof(S) * (size_t)kFirstDepth * O::SIZE * kTile + sizeof(unsigned long long) * 2 * kFirstDepth + 16;
       bool & attr_set = attr_set_[8]; // per engine: function attributes are per device
       if(!attr_set)
       {
         cudaFuncSetAttribute(forward_first_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
       }
-      launchPdl(forward_first_kernel<M>, dim3((B + kWarps * 32 - 1) / (kWarps * 32)), dim3(kWarps * 32), smem, st, model_,
-                ws_, prm_, fan_, iter);
+      launchPdl(forward_first_kernel<M>, dim3((B + kTile - 1) / kTile), dim3(64), smem, st, model_, ws_, prm_, fan_, iter);
     }
     {
       constexpr int kWarps = 4;

@@ -88,31 +88,170 @@ __device__ __forceinline__ void lineSearchFinish(const Workspace<S> & ws,
   writeTrace<S>(ws, b, iter, S(iter), cost_out, lambda, dlambda, alpha, k_rel_norm, actual, expected, ratio);
 }
 
-/** Phase 1: alpha_list[0] for every running instance. */
+constexpr int kFirstDepth = 4; //!< ring stages between the loader warp and the compute warp of phase 1
+
+/** forwardPass(alpha) (DDPSolver.hpp:537-560) for one instance per lane with the operands {x_i, u_i, k_i, K_i} of the
+    current trajectory delivered by the CTA's loader warp.  Same arithmetic, in the same order, as forwardRolloutRing /
+    forwardRollout => the same costs bit for bit. */
 template<class M>
-__global__ void forward_first_kernel(const __grid_constant__ M model,
-                                     const __grid_constant__ Workspace<typename M::Scalar> ws,
-                                     const __grid_constant__ SolverParams<typename M::Scalar> prm,
-                                     const __grid_constant__ FwdFanout<typename M::Scalar> fan,
-                                     int iter)
+__device__ __forceinline__ typename M::Scalar forwardRolloutFed(const M & model_in_constant_bank,
+                                                                const Workspace<typename M::Scalar> & ws,
+                                                                const SolverParams<typename M::Scalar> & prm,
+                                                                const typename M::Scalar * __restrict__ ring,
+                                                                unsigned long long * full,
+                                                                unsigned long long * empty,
+                                                                int lane,
+                                                                int b,
+                                                                int sel,
+                                                                typename M::Scalar alpha,
+                                                                bool work)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  using O = FwdOperands<NX, NU>;
+  const M model = model_in_constant_bank;
+  const S t0 = prm.t0;
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+  S * __restrict__ xn = ws.x[sel ^ 1];
+  S * __restrict__ un = ws.u[sel ^ 1];
+  S * __restrict__ cn = ws.cost[sel ^ 1];
+
+  Matrix<S, NX, 1> x;
+#pragma unroll
+  for(int d = 0; d < NX; d++) x[d] = ws.x[sel][(size_t)d * Bp + b];
+  if(work)
+  {
+#pragma unroll
+    for(int d = 0; d < NX; d++) xn[(size_t)d * Bp + b] = x[d]; // candidate x_list[0] (:540)
+  }
+  S * xs_ptr = xn + (size_t)NX * Bp + b;
+  S * us_ptr = un + b;
+  S * cs_ptr = cn + b;
+
+  S csum = S(0);
+  for(int i = 0; i < N; i++)
+  {
+    const int st = i % kFirstDepth;
+    mbarWait(&full[st], (unsigned)(i / kFirstDepth) & 1u);
+    S xr[NX], ur[NU], kr[NU], Kr[NU * NX];
+    const S * op = ring + (size_t)st * O::SIZE * kTile + lane;
+#pragma unroll
+    for(int d = 0; d < NX; d++) xr[d] = op[(size_t)(O::X + d) * kTile];
+#pragma unroll
+    for(int d = 0; d < NU; d++) ur[d] = op[(size_t)(O::U + d) * kTile];
+#pragma unroll
+    for(int d = 0; d < NU; d++) kr[d] = op[(size_t)(O::KFF + d) * kTile];
+#pragma unroll
+    for(int d = 0; d < NU * NX; d++) Kr[d] = op[(size_t)(O::KFB + d) * kTile];
+    mbarArrive(&empty[st]); // the operands are in registers: the loader may refill the stage
+
+    if(work)
+    {
+      Matrix<S, NU, 1> u;
+#pragma unroll
+      for(int c = 0; c < NU; c++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int j = 0; j < NX; j++) acc += Kr[c + j * NU] * (x[j] - xr[j]);
+        u[c] = (ur[c] + alpha * kr[c]) + acc; // u' = u + alpha k + K (x' - x)   (:545-546)
+        us_ptr[(size_t)c * Bp] = u[c];
+      }
+      const S t = t0 + i * model.dt();
+      const S c = model.runningCost(t, x, u);
+      x = model.stateEq(t, x, u);
+#pragma unroll
+      for(int d = 0; d < NX; d++) xs_ptr[(size_t)d * Bp] = x[d];
+      *cs_ptr = c;
+      csum += c;
+    }
+    xs_ptr += (size_t)NX * Bp;
+    us_ptr += (size_t)NU * Bp;
+    cs_ptr += Bp;
+  }
+  if(work)
+  {
+    const S c = model.terminalCost(t0 + N * model.dt(), x);
+    cn[(size_t)N * Bp + b] = c;
+    csum += c;
+  }
+  return csum;
+}
+
+/** Phase 1: alpha_list[0] for every running instance.  CTA = one 32-instance tile: warp 0 rolls out, warp 1 loads. */
+template<class M>
+__global__ void __launch_bounds__(64) forward_first_kernel(const __grid_constant__ M model,
+                                                           const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                                           const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                                           const __grid_constant__ FwdFanout<typename M::Scalar> fan,
+                                                           int iter)
 {
   pdlPrologue();
   using S = typename M::Scalar;
-  constexpr int DEPTH = 4;
+  constexpr int NX = M::NX, NU = M::NU;
+  using O = FwdOperands<NX, NU>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  S * ring = reinterpret_cast<S *>(smem_raw) + (size_t)warp * DEPTH * FwdOperands<M::NX, M::NU>::SIZE * 32;
+  S * ring = reinterpret_cast<S *>(smem_raw); // [kFirstDepth][O::SIZE][32]
+  unsigned long long * full =
+      reinterpret_cast<unsigned long long *>(smem_raw + sizeof(S) * (size_t)kFirstDepth * O::SIZE * kTile);
+  unsigned long long * empty = full + kFirstDepth;
+  if(threadIdx.x == 0)
+  {
+    for(int st = 0; st < kFirstDepth; st++)
+    {
+      mbarInit(&full[st], 32);
+      mbarInit(&empty[st], 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
 
-  const int bg = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bg = blockIdx.x * kTile + lane;
   const int b = (bg < ws.B) ? bg : (ws.B - 1);
   const bool active = (bg < ws.B) && (ws.status[b] == 0);
+  // both warps see the same 32 verdicts: uniform exit; the barrier also publishes the mbarrier initialisation
+  if(!__syncthreads_or(active)) return;
   const int sel = ws.sel[b];
+  const size_t Bp = ws.Bp;
+
+  if(warp == 1)
+  {
+    // loader: {x_i, u_i, k_i, K_i} of this lane's instance for steps 0 .. N-1
+    const S * row_ptr[O::SIZE];
+    long long row_stride[O::SIZE];
+#pragma unroll
+    for(int e = 0; e < O::SIZE; e++)
+    {
+      if(e < O::U)
+      {
+        row_ptr[e] = ws.x[sel] + (size_t)(e - O::X) * Bp + b;
+        row_stride[e] = (long long)NX * (long long)Bp;
+      }
+      else if(e < O::KFF)
+      {
+        row_ptr[e] = ws.u[sel] + (size_t)(e - O::U) * Bp + b;
+        row_stride[e] = (long long)NU * (long long)Bp;
+      }
+      else if(e < O::KFB)
+      {
+        row_ptr[e] = ws.kff + (size_t)(e - O::KFF) * Bp + b;
+        row_stride[e] = (long long)NU * (long long)Bp;
+      }
+      else
+      {
+        row_ptr[e] = ws.kfb + (size_t)(e - O::KFB) * Bp + b;
+        row_stride[e] = (long long)(NU * NX) * (long long)Bp;
+      }
+    }
+    loaderLoop<S, O::SIZE, kFirstDepth>(ring, full, empty, lane, prm.N, row_ptr, row_stride);
+    return;
+  }
+
   const bool work = active && prm.n_alpha > 0;
   const S alpha = prm.alpha_list[0];
-  const S cost_new =
-      forwardRolloutRing<M, 1, DEPTH>(model, ws, prm, ring, lane, 0, b, sel, alpha, work, work, work,
-                                      candidateBuffer<S>(ws, sel, b));
+  const S cost_new = forwardRolloutFed<M>(model, ws, prm, ring, full, empty, lane, b, sel, alpha, work);
   if(!active) return;
   const S cost_cur = ws.cost_sum[b];
   S actual = S(0), expected = S(0), ratio = S(0);

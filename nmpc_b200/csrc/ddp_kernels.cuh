@@ -519,6 +519,45 @@ __device__ __forceinline__ void mbarArrive(unsigned long long * bar)
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
 }
 
+/* Loader-warp staging (used by the FMPC sweeps F2 / F3 and by phase 1 of the phased line search): a second warp of the
+   CTA streams the rows a step needs into a shared-memory ring with per-lane cp.async from running pointers -- no
+   registers, many loads in flight, running ahead by the ring depth -- and the copies' completion lands on a `full`
+   mbarrier (32 arrivals: every lane's copies of its own column); the compute warp releases a stage on `empty`. */
+__device__ __forceinline__ void cpAsyncArriveOn(unsigned long long * bar)
+{
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
+}
+
+/** Loader side: rows 0 .. ROWS-1 of `n_fills` consecutive steps.  row_ptr[r] = address of this lane's element of row r
+    for the FIRST step, advanced by row_stride[r] (signed, in scalars) per step. */
+template<class S, int ROWS, int DEPTH>
+__device__ __forceinline__ void loaderLoop(S * ring,
+                                           unsigned long long * full,
+                                           unsigned long long * empty,
+                                           int lane,
+                                           int n_fills,
+                                           const S * (&row_ptr)[ROWS],
+                                           const long long (&row_stride)[ROWS])
+{
+  for(int f = 0; f < n_fills; f++)
+  {
+    const int st = f % DEPTH;
+    if(f >= DEPTH) mbarWait(&empty[st], (unsigned)((f / DEPTH) - 1) & 1u); // the compute warp is done with it
+    S * dst = ring + (size_t)st * ROWS * kTile + lane;
+#pragma unroll
+    for(int r = 0; r < ROWS; r++)
+    {
+      if constexpr(sizeof(S) == 8)
+        cpAsync8(dst + (size_t)r * kTile, row_ptr[r]);
+      else
+        cpAsync4(dst + (size_t)r * kTile, row_ptr[r]);
+      row_ptr[r] += row_stride[r];
+    }
+    cpAsyncArriveOn(&full[st]);
+  }
+}
+
 /** Where a backward sweep gets the derivative tile of step i from.  TmaFeed: K1 wrote the tiles to HBM, lane 0 fetches
     step i-1 with one bulk (TMA) copy into a two-stage ring while step i computes. */
 template<class S, int SIZE>

@@ -41,40 +41,8 @@ using ddp::kTile;
    ahead by the ring depth), completion lands on a `full` mbarrier through cp.async.mbarrier.arrive.noinc (32 arrivals:
    every lane's copies of its own column); the compute warp releases a stage on an `empty` mbarrier.  Layouts in HBM
    stay the plain batch-innermost ones. */
-__device__ __forceinline__ void cpAsyncArriveOn(unsigned long long * bar)
-{
-  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
-}
-
-/** Loader side: rows 0 .. ROWS-1 of `n_fills` consecutive steps.  row_ptr[r] = address of this lane's element of row r
-    for the FIRST step, advanced by row_stride[r] (signed, in scalars) per step. */
-template<class S, int ROWS, int DEPTH>
-__device__ __forceinline__ void loaderLoop(S * ring,
-                                           unsigned long long * full,
-                                           unsigned long long * empty,
-                                           int lane,
-                                           int n_fills,
-                                           const S * (&row_ptr)[ROWS],
-                                           const long long (&row_stride)[ROWS])
-{
-  for(int f = 0; f < n_fills; f++)
-  {
-    const int st = f % DEPTH;
-    if(f >= DEPTH) ddp::mbarWait(&empty[st], (unsigned)((f / DEPTH) - 1) & 1u); // the compute warp is done with it
-    S * dst = ring + (size_t)st * ROWS * kTile + lane;
-#pragma unroll
-    for(int r = 0; r < ROWS; r++)
-    {
-      if constexpr(sizeof(S) == 8)
-        ddp::cpAsync8(dst + (size_t)r * kTile, row_ptr[r]);
-      else
-        ddp::cpAsync4(dst + (size_t)r * kTile, row_ptr[r]);
-      row_ptr[r] += row_stride[r];
-    }
-    cpAsyncArriveOn(&full[st]);
-  }
-}
+using ddp::cpAsyncArriveOn;
+using ddp::loaderLoop;
 
 constexpr int kTraceFields = 5; // iter, kkt_error, barrier_eps, alpha_s, alpha_nu
 
