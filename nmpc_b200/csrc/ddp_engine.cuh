@@ -727,11 +727,10 @@ protected:
       launchPdl(forward_first_kernel<M>, dim3((B + kTile - 1) / kTile), dim3(64), smem, st, model_, ws_, prm_, fan_, iter);
     }
     {
-      constexpr int kWarps = 4;
-      constexpr int ipw = 32 / kFanLanes;
-      const size_t smem = sizeof(S) * (size_t)kWarps * 4 * O::SIZE * ipw;
-      const int grid = (B + kWarps * ipw - 1) / (kWarps * ipw); // worst case: every instance listed
-      launchPdl(forward_fanout_kernel<M>, dim3(grid), dim3(kWarps * 32), smem, st, model_, ws_, prm_, fan_, iter);
+      constexpr int ipc = kFanWarps * (32 / kFanLanes); // listed instances per CTA
+      const size_t smem = sizeof(S) * (size_t)kFanDepth * ipc * O::SIZE + sizeof(unsigned long long) * 2 * kFanDepth + 16;
+      const int grid = (B + ipc - 1) / ipc; // worst case: every instance listed
+      launchPdl(forward_fanout_kernel<M>, dim3(grid), dim3((kFanWarps + 1) * 32), smem, st, model_, ws_, prm_, fan_, iter);
     }
   }
 

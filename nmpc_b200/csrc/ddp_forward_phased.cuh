@@ -268,41 +268,185 @@ __global__ void __launch_bounds__(64) forward_first_kernel(const __grid_constant
   fan.list[slot] = b;
 }
 
-/** Phase 2: candidates 1 .. n_alpha-1 of every listed instance at once. */
+constexpr int kFanWarps = 4; //!< compute warps of a phase-2 CTA (one more warp loads)
+constexpr int kFanDepth = 4; //!< ring stages between its loader warp and its compute warps
+
+/** Phase 2: candidates 1 .. n_alpha-1 of every listed instance at once.  CTA = 4 compute warps (16 lanes per listed
+    instance, two instances per warp) + 1 loader warp that streams {x_i, u_i, k_i, K_i} of the CTA's eight instances into
+    a shared-memory ring (per-lane cp.async, full / empty mbarriers); every lane of a group reads its instance's
+    operands from the ring as a broadcast. */
 template<class M>
-__global__ void forward_fanout_kernel(const __grid_constant__ M model,
-                                      const __grid_constant__ Workspace<typename M::Scalar> ws,
-                                      const __grid_constant__ SolverParams<typename M::Scalar> prm,
-                                      const __grid_constant__ FwdFanout<typename M::Scalar> fan,
-                                      int iter)
+__global__ void __launch_bounds__((kFanWarps + 1) * 32)
+    forward_fanout_kernel(const __grid_constant__ M model_in_constant_bank,
+                          const __grid_constant__ Workspace<typename M::Scalar> ws,
+                          const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                          const __grid_constant__ FwdFanout<typename M::Scalar> fan,
+                          int iter)
 {
   pdlPrologue();
   using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  using O = FwdOperands<NX, NU>;
   constexpr int GA = kFanLanes;
-  constexpr int IPW = 32 / GA;
-  constexpr int DEPTH = 4;
+  constexpr int IPW = 32 / GA; // listed instances per compute warp
+  constexpr int IPC = kFanWarps * IPW; // ... per CTA
+  constexpr int ROWS = IPC * O::SIZE; // ring rows of one step: [instance of the CTA][operand]
   constexpr unsigned kFull = 0xffffffffu;
   constexpr unsigned kGroupMask = (1u << GA) - 1u;
   const int count = *fan.count;
+  const int cta_slot0 = blockIdx.x * IPC;
+  if(cta_slot0 >= count) return; // CTA-uniform
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S * ring = reinterpret_cast<S *>(smem_raw); // [kFanDepth][ROWS]
+  unsigned long long * full = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(S) * (size_t)kFanDepth * ROWS);
+  unsigned long long * empty = full + kFanDepth;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int warp_slot0 = (blockIdx.x * (blockDim.x >> 5) + warp) * IPW;
-  if(warp_slot0 >= count) return; // warp-uniform
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  S * ring = reinterpret_cast<S *>(smem_raw) + (size_t)warp * DEPTH * FwdOperands<M::NX, M::NU>::SIZE * IPW;
+  if(threadIdx.x == 0)
+  {
+    for(int st = 0; st < kFanDepth; st++)
+    {
+      mbarInit(&full[st], 32);
+      mbarInit(&empty[st], kFanWarps * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
 
+  if(warp == kFanWarps)
+  {
+    // loader: lane l streams ring rows l, l + 32, ...; row = (instance of the CTA) * O::SIZE + operand
+    constexpr int RPL = (ROWS + 31) / 32;
+    const S * row_ptr[RPL];
+    long long row_stride[RPL];
+#pragma unroll
+    for(int q = 0; q < RPL; q++)
+    {
+      const int row = q * 32 + lane;
+      const int inst = (row < ROWS) ? row / O::SIZE : 0;
+      const int e = (row < ROWS) ? row % O::SIZE : 0;
+      const int slot = cta_slot0 + inst;
+      const int b = fan.list[slot < count ? slot : cta_slot0]; // surplus slots repeat a valid instance
+      const int sel = ws.sel[b];
+      if(e < O::U)
+      {
+        row_ptr[q] = ws.x[sel] + (size_t)(e - O::X) * Bp + b;
+        row_stride[q] = (long long)NX * (long long)Bp;
+      }
+      else if(e < O::KFF)
+      {
+        row_ptr[q] = ws.u[sel] + (size_t)(e - O::U) * Bp + b;
+        row_stride[q] = (long long)NU * (long long)Bp;
+      }
+      else if(e < O::KFB)
+      {
+        row_ptr[q] = ws.kff + (size_t)(e - O::KFF) * Bp + b;
+        row_stride[q] = (long long)NU * (long long)Bp;
+      }
+      else
+      {
+        row_ptr[q] = ws.kfb + (size_t)(e - O::KFB) * Bp + b;
+        row_stride[q] = (long long)(NU * NX) * (long long)Bp;
+      }
+    }
+    for(int f = 0; f < N; f++)
+    {
+      const int st = f % kFanDepth;
+      if(f >= kFanDepth) mbarWait(&empty[st], (unsigned)((f / kFanDepth) - 1) & 1u);
+#pragma unroll
+      for(int q = 0; q < RPL; q++)
+      {
+        const int row = q * 32 + lane;
+        if(row < ROWS)
+        {
+          if constexpr(sizeof(S) == 8)
+            cpAsync8(ring + (size_t)st * ROWS + row, row_ptr[q]);
+          else
+            cpAsync4(ring + (size_t)st * ROWS + row, row_ptr[q]);
+        }
+        row_ptr[q] += row_stride[q];
+      }
+      cpAsyncArriveOn(&full[st]);
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ compute warps
+  const M model = model_in_constant_bank;
+  const S t0 = prm.t0;
   const int g = lane / GA;
   const int a = lane % GA;
-  const int slot = warp_slot0 + g;
+  const int inst = warp * IPW + g; // instance of the CTA
+  const int slot = cta_slot0 + inst;
   const bool valid = slot < count;
-  const int b = valid ? fan.list[slot] : fan.list[warp_slot0];
+  const int b = fan.list[valid ? slot : cta_slot0];
   const int sel = ws.sel[b];
   const int rem = prm.n_alpha - 1;
   const bool work = valid && (a < rem);
   const S my_alpha = prm.alpha_list[work ? (1 + a) : 0];
-  const size_t item = (size_t)slot * GA + a;
-  const FwdDest<S> dst{fan.sx, fan.su, fan.sc, fan.items, item};
-  const S my_cost = forwardRolloutRing<M, GA, DEPTH>(model, ws, prm, ring, g, a, b, sel, my_alpha, work, work, valid, dst);
+  const size_t item = (size_t)slot * GA + a; // scratch column of this candidate
+  const size_t Bd = fan.items;
+
+  Matrix<S, NX, 1> x;
+#pragma unroll
+  for(int d = 0; d < NX; d++) x[d] = ws.x[sel][(size_t)d * Bp + b];
+  if(work)
+  {
+#pragma unroll
+    for(int d = 0; d < NX; d++) fan.sx[(size_t)d * Bd + item] = x[d];
+  }
+  S * xs_ptr = fan.sx + (size_t)NX * Bd + item;
+  S * us_ptr = fan.su + item;
+  S * cs_ptr = fan.sc + item;
+  S my_cost = S(0);
+  for(int i = 0; i < N; i++)
+  {
+    const int st = i % kFanDepth;
+    mbarWait(&full[st], (unsigned)(i / kFanDepth) & 1u);
+    S xr[NX], ur[NU], kr[NU], Kr[NU * NX];
+    const S * op = ring + (size_t)st * ROWS + (size_t)inst * O::SIZE; // same address in the whole group: broadcast
+#pragma unroll
+    for(int d = 0; d < NX; d++) xr[d] = op[O::X + d];
+#pragma unroll
+    for(int d = 0; d < NU; d++) ur[d] = op[O::U + d];
+#pragma unroll
+    for(int d = 0; d < NU; d++) kr[d] = op[O::KFF + d];
+#pragma unroll
+    for(int d = 0; d < NU * NX; d++) Kr[d] = op[O::KFB + d];
+    mbarArrive(&empty[st]);
+
+    if(work)
+    {
+      Matrix<S, NU, 1> u;
+#pragma unroll
+      for(int c = 0; c < NU; c++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int j = 0; j < NX; j++) acc += Kr[c + j * NU] * (x[j] - xr[j]);
+        u[c] = (ur[c] + my_alpha * kr[c]) + acc; // u' = u + alpha k + K (x' - x)   (:545-546)
+        us_ptr[(size_t)c * Bd] = u[c];
+      }
+      const S t = t0 + i * model.dt();
+      const S c = model.runningCost(t, x, u);
+      x = model.stateEq(t, x, u);
+#pragma unroll
+      for(int d = 0; d < NX; d++) xs_ptr[(size_t)d * Bd] = x[d];
+      *cs_ptr = c;
+      my_cost += c;
+    }
+    xs_ptr += (size_t)NX * Bd;
+    us_ptr += (size_t)NU * Bd;
+    cs_ptr += Bd;
+  }
+  if(work)
+  {
+    const S c = model.terminalCost(t0 + N * model.dt(), x);
+    fan.sc[(size_t)N * Bd + item] = c;
+    my_cost += c;
+  }
 
   const S cost_cur = ws.cost_sum[b];
   S my_actual = S(0), my_expected = S(0), my_ratio = S(0);
@@ -313,12 +457,12 @@ __global__ void forward_fanout_kernel(const __grid_constant__ M model,
   const unsigned ok_ballot = __ballot_sync(kFull, ok);
   const unsigned gm = (ok_ballot >> (g * GA)) & kGroupMask;
   const int pick = (gm != 0) ? (__ffs(gm) - 1) : (rem - 1); // first success, else the last candidate tried
-  const int src = g * GA + pick;
-  const S r_actual = __shfl_sync(kFull, my_actual, src);
-  const S r_expected = __shfl_sync(kFull, my_expected, src);
-  const S r_ratio = __shfl_sync(kFull, my_ratio, src);
-  const S r_cost = __shfl_sync(kFull, my_cost, src);
-  const S r_alpha = __shfl_sync(kFull, my_alpha, src);
+  const int src_lane = g * GA + pick;
+  const S r_actual = __shfl_sync(kFull, my_actual, src_lane);
+  const S r_expected = __shfl_sync(kFull, my_expected, src_lane);
+  const S r_ratio = __shfl_sync(kFull, my_ratio, src_lane);
+  const S r_cost = __shfl_sync(kFull, my_cost, src_lane);
+  const S r_alpha = __shfl_sync(kFull, my_alpha, src_lane);
   const bool success = valid && (gm != 0);
   if(valid && a == 0)
   {
@@ -332,9 +476,6 @@ __global__ void forward_fanout_kernel(const __grid_constant__ M model,
   __syncwarp();
   if(success)
   {
-    constexpr int NX = M::NX, NU = M::NU;
-    const int N = prm.N;
-    const size_t Bp = ws.Bp;
     const size_t win = (size_t)slot * GA + pick;
     const int rows_x = (N + 1) * NX, rows_u = N * NU, rows_c = N + 1;
     S * __restrict__ dx = ws.x[sel ^ 1];
