@@ -695,13 +695,17 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
     u_nxt[a] = us[((size_t)(N > 1 ? N - 2 : 0) * NU + a) * Bp + b];
   }
   bool ok = true;
+  // running pointers (step N-1 first, one step back per iteration) instead of per-step 64-bit address arithmetic
+  S * kff_ptr = ws.kff + (size_t)(N - 1) * NU * Bp + b;
+  S * kfb_ptr = ws.kfb + (size_t)(N - 1) * NU * NX * Bp + b;
+  const S * u2_ptr = us + (size_t)(N > 2 ? N - 3 : 0) * NU * Bp + b; // u of step i - 2
 
   for(int i = N - 1; i >= 0; i--)
   {
     {
-      const int ip = (i > 1) ? i - 2 : 0;
 #pragma unroll
-      for(int a = 0; a < NU; a++) u_nx2[a] = us[((size_t)ip * NU + a) * Bp + b];
+      for(int a = 0; a < NU; a++) u_nx2[a] = u2_ptr[(size_t)a * Bp];
+      if(i > 2) u2_ptr -= (size_t)NU * Bp;
     }
     const S * const blk = feed.acquire(i);
     if(work && ok)
@@ -996,13 +1000,13 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
 #pragma unroll
     for(int a = 0; a < NU; a++)
     {
-      ws.kff[((size_t)i * NU + a) * Bp + b] = k[a];
+      kff_ptr[(size_t)a * Bp] = k[a];
       kn += k[a] * k[a];
       const S uv = u_cur[a];
       un += uv * uv;
     }
 #pragma unroll
-    for(int d = 0; d < NU * NX; d++) ws.kfb[((size_t)i * NU * NX + d) * Bp + b] = K[d];
+    for(int d = 0; d < NU * NX; d++) kfb_ptr[(size_t)d * Bp] = K[d];
     {
       // |k| / (|u| + 1) > num / den  <=>  |k| * den > num * (|u| + 1)   (both denominators >= 1)
       const S a_num = (NU == 1) ? fabs(k[0]) : sqrt(kn);
@@ -1016,6 +1020,8 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
       } while(0);
     }
     feed.release();
+    kff_ptr -= (size_t)NU * Bp;
+    kfb_ptr -= (size_t)NU * NX * Bp;
 #pragma unroll
     for(int a = 0; a < NU; a++)
     {
