@@ -518,7 +518,13 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
   }
 
   bool llt_failed = false;
-  for(int i = N - 1; i >= 0; i--)
+  // running store pointers (step N-1 first) instead of per-step 64-bit address arithmetic
+  S * kff_ptr = ws.kff + (size_t)(N - 1) * NU * Bp + b;
+  S * kfb_ptr = ws.kfb + (size_t)(N - 1) * NU * NX * Bp + b;
+  S * sv_ptr = ws.sv + (size_t)(N - 1) * NX * Bp + b;
+  S * P_ptr = ws.P + (size_t)(N - 1) * NX * NX * Bp + b;
+  for(int i = N - 1; i >= 0; i--, kff_ptr -= (size_t)NU * Bp, kfb_ptr -= (size_t)NU * NX * Bp, sv_ptr -= (size_t)NX * Bp,
+          P_ptr -= (size_t)NX * NX * Bp)
   {
     const int st = (N - 1 - i) % R2::kDepth;
     const unsigned use = (unsigned)((N - 1 - i) / R2::kDepth);
@@ -783,25 +789,25 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
 #pragma unroll
     for(int d = 0; d < NU; d++)
     {
-      ws.kff[((size_t)i * NU + d) * Bp + b] = k[d];
+      kff_ptr[(size_t)d * Bp] = k[d];
       nan_probe += k[d] * S(0);
     }
 #pragma unroll
     for(int d = 0; d < NU * NX; d++)
     {
-      ws.kfb[((size_t)i * NU * NX + d) * Bp + b] = K[d];
+      kfb_ptr[(size_t)d * Bp] = K[d];
       nan_probe += K[d] * S(0);
     }
 #pragma unroll
     for(int d = 0; d < NX; d++)
     {
-      ws.sv[((size_t)i * NX + d) * Bp + b] = sv[d];
+      sv_ptr[(size_t)d * Bp] = sv[d];
       nan_probe += sv[d] * S(0);
     }
 #pragma unroll
     for(int d = 0; d < NX * NX; d++)
     {
-      ws.P[((size_t)i * NX * NX + d) * Bp + b] = P[d];
+      P_ptr[(size_t)d * Bp] = P[d];
       nan_probe += P[d] * S(0) + A[d] * S(0);
     }
 #pragma unroll
@@ -937,7 +943,14 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
   S nan_probe = S(0);
   S alpha_s_max = S(1), alpha_nu_max = S(1);
   const S margin_ratio = S(0.995);
-  for(int i = 0; i <= N; i++)
+  // running store pointers instead of per-step 64-bit address arithmetic
+  S * dlam_ptr = ws.dlam + b;
+  S * dx_ptr = ws.dx + b;
+  S * du_ptr = ws.du + b;
+  S * ds_ptr = ws.ds + b;
+  S * dnu_ptr = ws.dnu + b;
+  for(int i = 0; i <= N; i++, dlam_ptr += (size_t)NX * Bp, dx_ptr += (size_t)NX * Bp, du_ptr += (size_t)NU * Bp,
+          ds_ptr += (size_t)NG * Bp, dnu_ptr += (size_t)NG * Bp)
   {
     const int st = i % R3::kDepth;
     ddp::mbarWait(&full[st], (unsigned)(i / R3::kDepth) & 1u); // operands of step i (ForwardRows) have landed
@@ -955,8 +968,8 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
 #pragma unroll
       for(int q = 0; q < NX; q++) acc += op[(size_t)(R3::P + r + q * NX) * kTile] * dx[q];
       const S dl = acc - op[(size_t)(R3::SV + r) * kTile];
-      ws.dlam[((size_t)i * NX + r) * Bp + b] = dl;
-      ws.dx[((size_t)i * NX + r) * Bp + b] = dx[r];
+      dlam_ptr[(size_t)r * Bp] = dl;
+      dx_ptr[(size_t)r * Bp] = dx[r];
       nan_probe += dl * S(0) + dx[r] * S(0);
     }
     if(i == N) break;
@@ -970,7 +983,7 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
 #pragma unroll
       for(int q = 0; q < NX; q++) acc += op[(size_t)(R3::KFB + r + q * NU) * kTile] * dx[q];
       du[r] = acc + op[(size_t)(R3::KFF + r) * kTile];
-      ws.du[((size_t)i * NU + r) * Bp + b] = du[r];
+      du_ptr[(size_t)r * Bp] = du[r];
       nan_probe += du[r] * S(0);
     }
     // ds_i = -(C dx + D du + g_bar) ; dnu_i = -(nu (ds + s) - eps) / s               (2.27a-b)
@@ -986,8 +999,8 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
       const S sj = op[(size_t)(R3::S_ + j) * kTile];
       const S nj = op[(size_t)(R3::NU_ + j) * kTile];
       const S dnj = S(-1) * (nj * (dsj + sj) - barrier_eps) / sj;
-      ws.ds[((size_t)i * NG + j) * Bp + b] = dsj;
-      ws.dnu[((size_t)i * NG + j) * Bp + b] = dnj;
+      ds_ptr[(size_t)j * Bp] = dsj;
+      dnu_ptr[(size_t)j * Bp] = dnj;
       nan_probe += dsj * S(0) + dnj * S(0);
       // fraction-to-boundary (:729-736).  The quotients are formed unconditionally and selected afterwards: same
       // values where they are used, but the 2 x NG divisions of a step become independent instruction streams the
