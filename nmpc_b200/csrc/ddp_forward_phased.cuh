@@ -130,7 +130,8 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutFed(const M & model_
   S * cs_ptr = cn + b;
 
   S csum = S(0);
-  for(int i = 0; i < N; i++)
+  S fi = S(0); // == S(i) exactly: spares the int -> floating-point conversion of `i * dt` on every step
+  for(int i = 0; i < N; i++, fi += S(1))
   {
     const int st = i % kFirstDepth;
     mbarWait(&full[st], (unsigned)(i / kFirstDepth) & 1u);
@@ -158,7 +159,7 @@ __device__ __forceinline__ typename M::Scalar forwardRolloutFed(const M & model_
         u[c] = (ur[c] + alpha * kr[c]) + acc; // u' = u + alpha k + K (x' - x)   (:545-546)
         us_ptr[(size_t)c * Bp] = u[c];
       }
-      const S t = t0 + i * model.dt();
+      const S t = t0 + fi * model.dt();
       const S c = model.runningCost(t, x, u);
       x = model.stateEq(t, x, u);
 #pragma unroll
@@ -401,7 +402,8 @@ __global__ void __launch_bounds__((kFanWarps + 1) * 32)
   S * us_ptr = fan.su + item;
   S * cs_ptr = fan.sc + item;
   S my_cost = S(0);
-  for(int i = 0; i < N; i++)
+  S fi = S(0); // == S(i) exactly
+  for(int i = 0; i < N; i++, fi += S(1))
   {
     const int st = i % kFanDepth;
     mbarWait(&full[st], (unsigned)(i / kFanDepth) & 1u);
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__((kFanWarps + 1) * 32)
         u[c] = (ur[c] + my_alpha * kr[c]) + acc; // u' = u + alpha k + K (x' - x)   (:545-546)
         us_ptr[(size_t)c * Bd] = u[c];
       }
-      const S t = t0 + i * model.dt();
+      const S t = t0 + fi * model.dt();
       const S c = model.runningCost(t, x, u);
       x = model.stateEq(t, x, u);
 #pragma unroll
