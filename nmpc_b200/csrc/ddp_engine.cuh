@@ -89,10 +89,13 @@ public:
     NMPC_CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     NMPC_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&h_counter_), sizeof(int)));
     Bp_ = ((capacity_ + 127) / 128) * 128;
-    NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)backwardSmemBytes(maxThreadsPerBlock())));
-    NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)backwardSmemBytes(maxThreadsPerBlock())));
+    if(kThreadSweepFits)
+    {
+      NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)backwardSmemBytes(maxThreadsPerBlock())));
+      NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)backwardSmemBytes(maxThreadsPerBlock())));
+    }
     applyConfig(cfg, true);
   }
 
@@ -535,10 +538,13 @@ protected:
   static constexpr int kCoopGS = (NX <= 1) ? 1 : (NX <= 2) ? 2 : (NX <= 4) ? 4 : (NX <= 8) ? 8 : (NX <= 16) ? 16 : 32;
 
   /** K2 stages two derivative blocks per thread in shared memory (cp.async ring). */
-  static size_t backwardSmemBytes(int tpb)
+  static constexpr size_t backwardSmemBytes(int tpb)
   {
     return 2 * sizeof(S) * (size_t)L::SIZE * tpb + 16 * (size_t)(tpb / 32) + 128;
   }
+  // the thread-per-instance sweep needs that ring for at least one warp; for large n_u (centroidal motion, 9 x 16:
+  // 374 KB per warp) it does not fit an SM's shared memory and the cooperative sweep is the only K2 variant
+  static constexpr bool kThreadSweepFits = backwardSmemBytes(32) <= 227 * 1024;
 
   /** K3 variant: lanes per instance that evaluate line-search candidates concurrently.  Small
       batches cannot fill the 148 SMs with one thread per instance, so they spend lanes on speculation. */
@@ -559,6 +565,7 @@ protected:
   /** K2 variant: lanes per instance (columns of the n_x x n_x matrices are spread over the group). */
   static int backwardLanesPerInstance(int B)
   {
+    if(!kThreadSweepFits) return kCoopGS;
     if(const char * env = std::getenv("NMPC_B200_BWD_GS"))
     {
       int v = std::atoi(env);

@@ -321,6 +321,11 @@ int oracle_model_dims(const char * model, int * nx, int * nu, int * ng, int * np
     *nx = 2, *nu = 2, *ng = 0, *nparams = DDPProblemVerticalMotion::kNumParams;
     return 0;
   }
+  if(m == "centroidal_motion")
+  {
+    *nx = 9, *nu = 16, *ng = 0, *nparams = DDPProblemCentroidalMotion::kNumParams;
+    return 0;
+  }
   if(m == "fmpc_cartpole")
   {
     *nx = 4, *nu = 1, *ng = 4, *nparams = FmpcProblemCartPole::kNumParams;
@@ -345,6 +350,8 @@ int oracle_model_default_params(const char * model, double * params)
     DDPProblemQuadrotor::defaultParams(params);
   else if(m == "vertical_motion")
     DDPProblemVerticalMotion::defaultParams(params);
+  else if(m == "centroidal_motion")
+    DDPProblemCentroidalMotion::defaultParams(params);
   else if(m == "fmpc_cartpole")
     FmpcProblemCartPole::defaultParams(params);
   else if(m == "fmpc_oscillator")
@@ -393,6 +400,10 @@ int oracle_ddp_solve_batch(const char * model,
     return ddpSolveBatch<DDPProblemVerticalMotion, 2, 2>(params, cfg, B, t0, x0, u_init, u_lo, u_hi, x_out, u_out,
                                                          cost_out, k_out, K_out, trace_out, n_trace_out, status_out,
                                                          iters_out, n_fwd_out, n_bwd_out, nthreads);
+  if(m == "centroidal_motion")
+    return ddpSolveBatch<DDPProblemCentroidalMotion, 9, 16>(params, cfg, B, t0, x0, u_init, u_lo, u_hi, x_out, u_out,
+                                                            cost_out, k_out, K_out, trace_out, n_trace_out, status_out,
+                                                            iters_out, n_fwd_out, n_bwd_out, nthreads);
   return -2;
 }
 
@@ -446,6 +457,9 @@ int oracle_model_eval(const char * model,
   if(m == "vertical_motion")
     return modelEval<DDPProblemVerticalMotion, 2, 2>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx,
                                                      Vxx);
+  if(m == "centroidal_motion")
+    return modelEval<DDPProblemCentroidalMotion, 9, 16>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx,
+                                                        Vxx);
   if(m == "fmpc_cartpole")
     return modelEval<FmpcProblemCartPole, 4, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
   if(m == "fmpc_oscillator")

@@ -633,6 +633,7 @@ protected:
 // ---- vertical motion with a time-varying input dimension (TestDDPVerticalMotion.cpp:25-234) ----
 // The functor of include/nmpc_b200/models/vertical_motion.h restates the problem bodies once for host and device;
 // what pins both is tests/golden/vertical_*: outputs of the reference's DDPSolver<2, Eigen::Dynamic> (oracle/ref).
+#include <nmpc_b200/models/centroidal_motion.h>
 #include <nmpc_b200/models/vertical_motion.h>
 
 namespace oracle
@@ -736,4 +737,7 @@ protected:
   F f_;
 };
 using DDPProblemVerticalMotion = DDPProblemFromFunctor<nmpc_b200::models::VerticalMotion<double>>;
+// centroidal motion, n_x = 9, input dimension 16 or 0 (TestDDPCentroidalMotion.cpp:18-201); pinned by
+// tests/golden/reference_centroidal.npz (the reference's DDPSolver<9, Eigen::Dynamic>, oracle/ref/ref_centroidal.cpp)
+using DDPProblemCentroidalMotion = DDPProblemFromFunctor<nmpc_b200::models::CentroidalMotion<double>>;
 } // namespace oracle

@@ -109,3 +109,19 @@ def vertical_mpc(horizon_steps, with_constraint, n_ticks, x0=(1.2, 0.0), t0=0.0)
     if rc != 0:
         raise RuntimeError("reference DDPSolver<2, Dynamic>::solve threw")
     return out
+
+
+def centroidal_mpc(horizon_steps, n_ticks, first_max_iter=500):
+    """TestDDPCentroidalMotion's MPC loop (TestDDPCentroidalMotion.cpp:238-353) with the reference's
+    DDPSolver<9, Eigen::Dynamic>: per-tick current_x, u_list[0] (padded to 16), its size, iterations; the full
+    trajectories and cost of the first solve and the trajectories of the last one (u padded to 16)."""
+    N, T = int(horizon_steps), int(n_ticks)
+    out = {"x_log": np.zeros((T, 9)), "u0_log": np.zeros((T, 16)), "dim_log": np.zeros(T, dtype=np.int32),
+           "iters_log": np.zeros(T, dtype=np.int32), "x_first": np.zeros((N + 1, 9)), "u_first": np.zeros((N, 16)),
+           "cost_first": np.zeros(1), "x": np.zeros((N + 1, 9)), "u": np.zeros((N, 16))}
+    rc = lib().ref_centroidal_mpc(N, int(first_max_iter), T, _p(out["x_log"]), _p(out["u0_log"]), _p(out["dim_log"]),
+                                  _p(out["iters_log"]), _p(out["x_first"]), _p(out["u_first"]), _p(out["cost_first"]),
+                                  _p(out["x"]), _p(out["u"]))
+    if rc != 0:
+        raise RuntimeError("reference DDPSolver<9, Dynamic>::solve threw")
+    return out
