@@ -20,6 +20,7 @@
 #include "ddp_kernels.cuh"
 #include "ddp_backward_coop.cuh"
 #include "ddp_backward_quad.cuh"
+#include "ddp_backward_wide.cuh"
 #include "ddp_backward_fused.cuh"
 #include "ddp_forward_phased.cuh"
 #include "ddp_mpc.cuh"
@@ -663,8 +664,46 @@ protected:
               ws_, prm_, iter);
   }
 
+  /** K2 variant for many inputs (n_u >= 8, no input limits): the n_u side spread over the lanes of a group
+      (ddp_backward_wide.cuh).  Measured on B200, centroidal motion 9 x 16, B = 1024, one sweep: see DESIGN.md;
+      NMPC_B200_BWD_WIDE=0 falls back to the cooperative variant that recomputes the n_u x n_u part in every lane. */
+  static constexpr int kWideGS = (NU <= 16 && NX < 16) ? 16 : 32;
+  static constexpr bool kWideOk = NU >= 8 && NU <= kWideGS && NX < kWideGS;
+  static bool backwardUsesWide()
+  {
+    if(const char * env = std::getenv("NMPC_B200_BWD_WIDE"))
+    {
+      if(env[0] == '0') return false;
+    }
+    return kWideOk;
+  }
+
+  void launchBackwardWide(int B, int iter, cudaStream_t st)
+  {
+    if constexpr(kWideOk)
+    {
+      using C = WideLayout<M, kWideGS>;
+      bool & attr_set = attr_set_[9]; // per engine: function attributes are per device
+      if(!attr_set)
+      {
+        NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_wide_kernel<M, kWideGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)C::bytes()));
+        attr_set = true;
+      }
+      launchPdl(backward_wide_kernel<M, kWideGS>, dim3((B + C::IPW - 1) / C::IPW), dim3(32), C::bytes(), st, ws_, prm_, iter);
+    }
+  }
+
   void launchBackward(int B, int tpb, int grid, int iter, cudaStream_t st)
   {
+    if constexpr(kWideOk)
+    {
+      if(!cfg_.with_input_constraint && backwardUsesWide())
+      {
+        launchBackwardWide(B, iter, st);
+        return;
+      }
+    }
     if constexpr(NX < 8)
     {
       if(use_fused_)
@@ -939,7 +978,7 @@ protected:
   int * h_counter_ = nullptr;
   std::vector<double> u_lo_, u_hi_;
   bool have_limits_ = false;
-  bool attr_set_[9] = {false, false, false, false, false, false, false, false, false};
+  bool attr_set_[10] = {false, false, false, false, false, false, false, false, false, false};
   bool use_fused_ = false; //!< K1 fused into K2 (decided once, at allocation)
   bool limits_vary_ = false; //!< the limits differ between horizon steps
   bool timing_ = false;

@@ -222,3 +222,43 @@ def test_device_mpc_loop(gpu):
     x_end = got["x"][:, -1]
     assert np.all(np.linalg.norm(x_end[:, :3] - ref_pos(TICKS * DT), axis=1) < 1e-2 + 0.03)  # instance 1 starts 2 cm off
     assert np.linalg.norm(x_end[0, :3] - ref_pos(TICKS * DT)) < 1e-2 and np.all(np.linalg.norm(x_end[:, 3:], axis=1) < 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reg_type", [1, 2])
+def test_device_wide_sweep_agrees_with_the_cooperative_sweep_and_the_oracle(gpu, reg_type, monkeypatch):
+    """K2 for many inputs (ddp_backward_wide.cuh, the default at n_u = 16) against the cooperative variant
+    (NMPC_B200_BWD_WIDE=0) and the oracle, both regularisation types, a ragged batch (odd number of instances: the
+    second half of the last warp idles)."""
+    p = O.default_params("centroidal_motion")
+    B = 7
+    x0 = np.repeat(X0, B, axis=0)
+    x0[:, :3] += np.random.default_rng(5).uniform(-0.05, 0.05, (B, 3))
+    u_init = np.zeros((B, N, 16))
+    kw = dict(max_iter=6, horizon_steps=N, reg_type=reg_type)
+    ref = O.ddp_solve_batch("centroidal_motion", p, O.ddp_config(**kw), x0, u_init)
+    out = {}
+    for tag, env in (("wide", None), ("coop", "0")):
+        if env is not None:
+            monkeypatch.setenv("NMPC_B200_BWD_WIDE", env)
+        solver = gpu.DDPSolver("centroidal_motion", params=p, batch_capacity=B)
+        c = solver.config()
+        c.horizon_steps, c.max_iter, c.reg_type = N, 6, reg_type
+        solver.solve_batch(0.0, x0, u_init)
+        out[tag] = (solver.controlData().u_list.copy(), solver.cost().copy(), solver.iterations().copy(),
+                    solver.K_list().copy(), solver.n_backward().copy())
+        solver.close()
+    umax = np.abs(ref["u"]).max()
+    _record(f"wide_vs_coop_reg{reg_type}", du_wide_vs_oracle_rel=np.abs(out["wide"][0] - ref["u"]).max() / umax,
+            du_coop_vs_oracle_rel=np.abs(out["coop"][0] - ref["u"]).max() / umax,
+            du_wide_vs_coop_rel=np.abs(out["wide"][0] - out["coop"][0]).max() / umax,
+            dK_wide_vs_coop=np.abs(out["wide"][3] - out["coop"][3]).max(), Kmax=np.abs(out["coop"][3]).max(),
+            dcost_wide_vs_oracle_rel=np.abs(out["wide"][1] / ref["cost"] - 1).max())
+    for tag in ("wide", "coop"):
+        np.testing.assert_allclose(out[tag][0], ref["u"], rtol=0, atol=1e-9 * umax, err_msg=tag)
+        # six iterations are mid-convergence: with reg_type 2 the cost of this ill-conditioned problem (input weight
+        # 1e-6) carries the FMA-contraction differences at 2e-11 (measured; 4e-14 with reg_type 1)
+        np.testing.assert_allclose(out[tag][1], ref["cost"], rtol=1e-12 if reg_type == 1 else 1e-9, atol=0, err_msg=tag)
+        assert np.array_equal(out[tag][2], ref["iters"]) and np.array_equal(out[tag][4], ref["n_bwd"])
+    # same expressions in the same order: the two device variants agree to the last bit
+    assert np.array_equal(out["wide"][0], out["coop"][0]) and np.array_equal(out["wide"][3], out["coop"][3])

@@ -3,7 +3,7 @@
 on one GPU: host buffers in, first controls out, best of 5 after 2 warm-ups.  Parity of the same runs is the job
 of tests/; this tool only reports time (gpurun_out/time_configs.json).
 
-    python tools/time_configs.py [quadrotor|fmpc|all]
+    python tools/time_configs.py [quadrotor|fmpc|fmpc_sweep|centroidal|all]
 """
 import json
 import os
@@ -56,6 +56,32 @@ def quadrotor():
     return out
 
 
+def centroidal():
+    """First solve of TestDDPCentroidalMotion (n_x = 9, n_u = 16 / 0, N = 100, reference termination rules) for a batch
+    of perturbed starts.  Not a BASELINE.json config: reported so that the cost of the untuned 9 x 16 kernels is on
+    record."""
+    N = 100
+    p = O.default_params("centroidal_motion")
+    out = {}
+    for B in (64, 1024):
+        x0 = np.zeros((B, 9))
+        x0[:, 2] = 1.0
+        x0[:, :3] += np.random.default_rng(B).uniform(-0.05, 0.05, (B, 3))
+        u0 = np.zeros((B, N, 16))
+        s = nmpc_b200.DDPSolver("centroidal_motion", params=p, batch_capacity=B)
+        s.config().horizon_steps = N
+        t = best_of(lambda: s.solve_batch(0.0, x0, u0, read_status=False), s.synchronize, n=3, warm=1)
+        s.enable_timing(True)
+        s.solve_batch(0.0, x0, u0, read_status=False)
+        d = s.computationDuration()
+        out[f"centroidal_B{B}"] = {"batch": B, "horizon": N, "ms": 1e3 * t, "traj_per_s": B / t,
+                                   "iters_mean": float(s.iterations().mean()), "iters_max": int(s.iterations().max()),
+                                   "stage_ms": {k: d[k] for k in ("derivative", "backward", "forward", "setup", "solve")},
+                                   "status_counts": {int(k): int(v) for k, v in zip(*np.unique(s.status(), return_counts=True))}}
+        s.close()
+    return out
+
+
 def fmpc(B=1024):
     N = 100
     x0 = O.cartpole_x0(B, 3)
@@ -79,6 +105,8 @@ if __name__ == "__main__":
         res.update(quadrotor())
     if what in ("fmpc", "all"):
         res.update(fmpc())
+    if what == "centroidal":
+        res.update(centroidal())
     if what == "fmpc_sweep":
         res["fmpc_sweep"] = [fmpc(B)["fmpc_cartpole"] for B in (1024, 4096, 16384, 65536)]
     print(json.dumps(res))
