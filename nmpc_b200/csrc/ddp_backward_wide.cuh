@@ -32,7 +32,8 @@ struct WideLayout
   static_assert(NU <= GS && NX < GS && GS <= 32, "one lane per input and per state column, one more for k");
   static constexpr int IPW = 32 / GS; //!< instances per warp
   static constexpr int STAGE = L::SIZE + NU; //!< derivative block + u_i
-  static constexpr int DEPTH = 3; //!< ring slots: step i lives in slot i % DEPTH
+  static constexpr int DEPTH = 2; //!< ring slots: step i lives in slot i % DEPTH; one step (~15 us) of prefetch distance
+                                  //!< hides the load latency, and 50 KB per CTA keeps four CTAs (one per scheduler) on an SM
   static constexpr int RING = 0;
   static constexpr int VXX = RING + DEPTH * STAGE;
   static constexpr int VX = VXX + NX * NX;
