@@ -44,7 +44,8 @@ public:
   DDPProblem(double dt) : dt_(dt)
   {
     static_assert(StateDim > 0, "[DDP] Template param StateDim should be positive.");
-    static_assert(InputDim >= 0, "[DDP] Template param InputDim should be non-negative (dynamic size is not built yet).");
+    static_assert(InputDim >= 0, "[DDP] Template param InputDim should be non-negative: a time-varying input dimension is declared as the "
+                                 "LARGEST dimension plus inputDim(t) (see nmpc_b200/models/vertical_motion.h).");
   }
   virtual ~DDPProblem() = default;
 
@@ -131,6 +132,14 @@ public:
     return functor_;
   }
 
+  using Base::inputDim;
+  /** DDPProblem::inputDim(t) (reference DDPProblem.h:72-85): the functor's own inputDim(t) when it declares a
+      time-varying input dimension (inputs a >= inputDim(t) are padding), InputDim otherwise. */
+  int inputDim(double t) const override
+  {
+    return inputDimOf(functor_, t, 0);
+  }
+
   StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const override
   {
     return functor_.stateEq(t, x, u);
@@ -176,6 +185,17 @@ public:
   }
 
 protected:
+  template<class G>
+  static auto inputDimOf(const G & g, double t, int) -> decltype(g.inputDim(t))
+  {
+    return g.inputDim(t);
+  }
+  template<class G>
+  static int inputDimOf(const G &, double, long)
+  {
+    return F::NU;
+  }
+
   F functor_;
   nmpc_b200::DeviceFunctorBinding binding_;
 };

@@ -9,12 +9,52 @@
 #include <memory>
 
 #include <nmpc_b200/models/cartpole.h>
+#include <nmpc_b200/models/centroidal_motion.h>
+#include <nmpc_b200/models/vertical_motion.h>
 #include <nmpc_ddp/DDPSolver.h>
 #include <nmpc_fmpc/FmpcSolver.h>
 
 using CartPoleF = nmpc_b200::models::CartPole<double>;
 using DDPProblemCartPole = nmpc_ddp::FunctorProblem<CartPoleF>;
 using FmpcProblemCartPole = nmpc_fmpc::FunctorProblem<CartPoleF>;
+using DDPProblemCentroidalMotion = nmpc_ddp::FunctorProblem<nmpc_b200::models::CentroidalMotion<double>>;
+using DDPProblemVerticalMotion = nmpc_ddp::FunctorProblem<nmpc_b200::models::VerticalMotion<double>>;
+
+// TestDDPCentroidalMotion.CheckDerivative (TestDDPCentroidalMotion.cpp:355-411) through the host-side virtuals, and
+// DDPProblem::inputDim(t) of the two problems with a time-varying input dimension
+static int checkCentroidal()
+{
+  auto problem = std::make_shared<DDPProblemCentroidalMotion>("centroidal_motion");
+  double t = 0;
+  DDPProblemCentroidalMotion::StateDimVector x;
+  DDPProblemCentroidalMotion::InputDimVector u;
+  for(int i = 0; i < 9; i++) x[i] = std::sin(1.0 + i); // any point: the test draws a random one
+  for(int i = 0; i < 16; i++) u[i] = std::cos(2.0 + i);
+  DDPProblemCentroidalMotion::StateStateDimMatrix fx_a, fx_n;
+  DDPProblemCentroidalMotion::StateInputDimMatrix fu_a, fu_n;
+  problem->calcStateEqDeriv(t, x, u, fx_a, fu_a);
+  constexpr double deriv_eps = 1e-6;
+  for(int i = 0; i < problem->stateDim(); i++)
+  {
+    auto xp = x, xm = x;
+    xp[i] += deriv_eps, xm[i] -= deriv_eps;
+    auto d = problem->stateEq(t, xp, u) - problem->stateEq(t, xm, u);
+    for(int r = 0; r < 9; r++) fx_n(r, i) = d[r] / (2 * deriv_eps);
+  }
+  for(int i = 0; i < problem->inputDim(t); i++)
+  {
+    auto up = u, um = u;
+    up[i] += deriv_eps, um[i] -= deriv_eps;
+    auto d = problem->stateEq(t, x, up) - problem->stateEq(t, x, um);
+    for(int r = 0; r < 9; r++) fu_n(r, i) = d[r] / (2 * deriv_eps);
+  }
+  double ex = std::sqrt((fx_a - fx_n).squaredNorm()), eu = std::sqrt((fu_a - fu_n).squaredNorm());
+  std::printf("centroidal_deriv_err %.3e %.3e\n", ex, eu);
+  auto vertical = std::make_shared<DDPProblemVerticalMotion>("vertical_motion");
+  std::printf("input_dims %d %d %d %d %d %d\n", problem->inputDim(0.0), problem->inputDim(1.5), problem->inputDim(2.0),
+              vertical->inputDim(0.0), vertical->inputDim(2.5), vertical->inputDim(4.7));
+  return (ex < 1e-6 && eu < 1e-6) ? 0 : 1;
+}
 
 static int checkDerivative()
 {
@@ -50,6 +90,7 @@ static int checkDerivative()
 int main(int argc, char ** argv)
 {
   int rc = checkDerivative();
+  rc |= checkCentroidal();
   if(argc > 1 && std::strcmp(argv[1], "--host-only") == 0)
   {
     // no GPU: creating a solver must fail loudly (no CPU fallback)

@@ -35,6 +35,10 @@ def test_facade_compiles_and_fails_loudly_without_gpu(facade_bin, nmpc):
     d = _parse(r.stdout)
     ex, eu = (float(v) for v in d["deriv_err"].split())
     assert ex < 1e-6 and eu < 1e-6 and r.returncode == 0
+    # TestDDPCentroidalMotion.CheckDerivative (:355-411) and inputDim(t) of the Dynamic-dimension problems
+    ex, eu = (float(v) for v in d["centroidal_deriv_err"].split())
+    assert ex < 1e-6 and eu < 1e-6
+    assert d["input_dims"].split() == ["16", "0", "16", "1", "2", "0"]
     if nmpc.device_count() == 0:
         assert "no CPU fallback" in d["host_only_error"]
 
