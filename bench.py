@@ -138,7 +138,13 @@ def cpu_baseline(O, B, seed, mode, min_seconds, native=True):
         el = time.perf_counter() - t0
         if el >= min_seconds:
             break
+    # single-thread latency of one solve: 256 instances on one thread
+    n1 = min(256, B)
+    t1 = time.perf_counter()
+    O.ddp_solve_batch("cartpole", p, cfg, x0[:n1], u_init[:n1], native=native, outputs=False, nthreads=1)
+    ms1 = 1e3 * (time.perf_counter() - t1) / n1
     return {"value": done / el, "unit": UNIT, "cores": int(threads), "kind": "port",
+            "per_core": done / el / max(int(threads), 1), "single_thread_ms_per_solve": ms1,
             "sample": f"{done} cart-pole solves ({done // B} x the B={B} workload, mode {mode}) in {el:.1f} s, "
                       f"oracle/ built -O3 -march=native -fopenmp, one solver object per thread"}
 

@@ -53,9 +53,26 @@ class FmpcConfig(C.Structure):
     ]
 
 
+def _host_cpu_tag():
+    """Short hash of this host's CPU model and instruction-set flags: -march=native code must not travel."""
+    import hashlib
+
+    ident = []
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith(("model name", "flags")):
+                    ident.append(line.split(":", 1)[1].strip())
+                    if len(ident) == 2:
+                        break
+    except OSError:
+        pass
+    return hashlib.sha1("|".join(ident).encode()).hexdigest()[:10]
+
+
 def build(native=False):
     """Compile the oracle if needed; returns the path of the shared library."""
-    target = "_build/liboracle_native.so" if native else "_build/liboracle.so"
+    target = f"_build/liboracle_native_{_host_cpu_tag()}.so" if native else "_build/liboracle.so"
     subprocess.run(["make", "-s", "-C", _ORACLE_DIR, target], check=True)
     return os.path.join(_ORACLE_DIR, target)
 
