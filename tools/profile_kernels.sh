@@ -14,4 +14,9 @@ if [ "${PROFILE_COOP:-0}" = "1" ]; then
   NMPC_B200_BWD_GS=4 timeout 600 ncu $COMMON -k regex:'backward_coop_kernel' --launch-skip 36 --launch-count 1 -f \
       -o gpurun_out/prof_${TAG}_coop python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_${TAG}_coop.log 2>&1
 fi
+if [ "${PROFILE_WIDE:-0}" = "1" ]; then
+  # K2 for many inputs (centroidal motion 9 x 16, B = 1024): the 2nd sweep of the 2nd solve
+  timeout 300 ncu $COMMON -k regex:'backward_wide_kernel' --launch-skip 5 --launch-count 1 -f \
+      -o gpurun_out/prof_${TAG}_wide python tools/time_configs.py centroidal_profile > gpurun_out/prof_${TAG}_wide.log 2>&1
+fi
 ls -la gpurun_out/*.ncu-rep

@@ -3,7 +3,7 @@
 on one GPU: host buffers in, first controls out, best of 5 after 2 warm-ups.  Parity of the same runs is the job
 of tests/; this tool only reports time (gpurun_out/time_configs.json).
 
-    python tools/time_configs.py [quadrotor|fmpc|fmpc_sweep|centroidal|all]
+    python tools/time_configs.py [quadrotor|fmpc|fmpc_sweep|centroidal|centroidal_profile|all]
 """
 import json
 import os
@@ -82,6 +82,22 @@ def centroidal():
     return out
 
 
+def centroidal_profile(B=1024):
+    """Four full iterations (termination thresholds off) of the centroidal problem, three times: every K2 launch is
+    live, for `ncu -k regex:backward_wide_kernel --launch-skip 5 --launch-count 1` (tools/profile_kernels.sh)."""
+    N = 100
+    p = O.default_params("centroidal_motion")
+    x0 = np.zeros((B, 9))
+    x0[:, 2] = 1.0
+    x0[:, :3] += np.random.default_rng(B).uniform(-0.05, 0.05, (B, 3))
+    u0 = np.zeros((B, N, 16))
+    s = nmpc_b200.DDPSolver("centroidal_motion", params=p, batch_capacity=B)
+    c = s.config()
+    c.horizon_steps, c.max_iter, c.k_rel_norm_thre, c.cost_update_thre = N, 4, 0.0, 0.0
+    t = best_of(lambda: s.solve_batch(0.0, x0, u0, read_status=False), s.synchronize, n=2, warm=1)
+    return {"centroidal_profile": {"batch": B, "iters": 4, "ms": 1e3 * t, "bwd_passes_mean": float(s.n_backward().mean())}}
+
+
 def fmpc(B=1024):
     N = 100
     x0 = O.cartpole_x0(B, 3)
@@ -107,6 +123,8 @@ if __name__ == "__main__":
         res.update(fmpc())
     if what == "centroidal":
         res.update(centroidal())
+    if what == "centroidal_profile":
+        res.update(centroidal_profile())
     if what == "fmpc_sweep":
         res["fmpc_sweep"] = [fmpc(B)["fmpc_cartpole"] for B in (1024, 4096, 16384, 65536)]
     print(json.dumps(res))
