@@ -495,7 +495,16 @@ __global__ void backward_coop_kernel(const __grid_constant__ M model,
   while(__any_sync(kFull, need))
   {
     if(need) n_bwd++;
-    const bool ok = backwardSweepCoop<M, GS, CONSTRAINED>(model, ws, prm, b, j, us, sm, need, lambda, dV0, dV1, k_rel_norm);
+    // results are kept only for instances that needed this sweep: one that is waiting for its tile mates' lambda retry
+    // keeps the dV / k_rel_norm of its own successful sweep
+    S sw_dV0 = S(0), sw_dV1 = S(0), sw_krn = S(0);
+    const bool ok = backwardSweepCoop<M, GS, CONSTRAINED>(model, ws, prm, b, j, us, sm, need, lambda, sw_dV0, sw_dV1, sw_krn);
+    if(need)
+    {
+      dV0 = sw_dV0;
+      dV1 = sw_dV1;
+      k_rel_norm = sw_krn;
+    }
     if(need)
     {
       if(ok)

@@ -22,6 +22,7 @@
 #include "ddp_backward_quad.cuh"
 #include "ddp_backward_wide.cuh"
 #include "ddp_backward_fused.cuh"
+#include "ddp_backward_lanes.cuh"
 #include "ddp_forward_phased.cuh"
 #include "ddp_mpc.cuh"
 #include "registry.h"
@@ -531,6 +532,12 @@ protected:
     NMPC_CUDA_CHECK(cudaGetLastError());
   }
 
+  static int envInt(const char * name, int dflt)
+  {
+    const char * env = std::getenv(name);
+    return env != nullptr ? std::atoi(env) : dflt;
+  }
+
   static constexpr int kMaxThreadsPerBlock = 128;
   static constexpr bool kHasBoxQP = true;
   static constexpr size_t kQuadSmemLimit = 200 * 1024; //!< shared memory the column-split K2 may use per CTA
@@ -633,6 +640,48 @@ protected:
               iter);
   }
 
+  /** K1 + K2 with G lanes per instance (ddp_backward_lanes.cuh): n_x <= 4, latency-bound batches. */
+  static constexpr bool kLanesOk = NX <= 4;
+  template<bool CONSTRAINED, int P, class XCH, int TPC>
+  void launchBackwardLanesT(int B, int iter, cudaStream_t st, int slot)
+  {
+    if constexpr(kLanesOk)
+    {
+      using LL = LaneLayout<M>;
+      bool & attr_set = lanes_attr_set_[slot];
+      if(!attr_set)
+      {
+        NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_lanes_kernel<M, CONSTRAINED, P, XCH, TPC>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TPC * LL::bytes())));
+        attr_set = true;
+      }
+      const int tiles = (B + kTile - 1) / kTile;
+      launchPdl(backward_lanes_kernel<M, CONSTRAINED, P, XCH, TPC>, dim3((tiles + TPC - 1) / TPC),
+                dim3((LL::CW + P) * 32 * TPC), TPC * LL::bytes(), st, model_, ws_, prm_, iter);
+    }
+  }
+  template<bool CONSTRAINED>
+  void launchBackwardLanes(int B, int iter, cudaStream_t st)
+  {
+    if constexpr(kLanesOk)
+    {
+      using LL = LaneLayout<M>;
+      using XS = XchSmem<S, LL::G>;
+      using XH = XchShfl<S, LL::G>;
+      const int c = CONSTRAINED ? 4 : 0;
+      if(lanes_variant_ == 2)
+      {
+        if(lanes_tiles_per_cta_ == 2) launchBackwardLanesT<CONSTRAINED, 2, XH, 2>(B, iter, st, c + 3);
+        else launchBackwardLanesT<CONSTRAINED, 2, XH, 1>(B, iter, st, c + 2);
+      }
+      else
+      {
+        if(lanes_tiles_per_cta_ == 2) launchBackwardLanesT<CONSTRAINED, 2, XS, 2>(B, iter, st, c + 1);
+        else launchBackwardLanesT<CONSTRAINED, 2, XS, 1>(B, iter, st, c + 0);
+      }
+    }
+  }
+
   /** K2 variant for latency-bound batches: four warps per 32-instance tile (ddp_backward_quad.cuh). */
   static bool backwardUsesQuad(int B)
   {
@@ -706,6 +755,14 @@ protected:
     }
     if constexpr(NX < 8)
     {
+      if(use_fused_ && kLanesOk && lanes_variant_ != 0 && B <= lanes_max_batch_)
+      {
+        if(cfg_.with_input_constraint)
+          launchBackwardLanes<true>(B, iter, st);
+        else
+          launchBackwardLanes<false>(B, iter, st);
+        return;
+      }
       if(use_fused_)
       {
         if(cfg_.with_input_constraint)
@@ -980,6 +1037,10 @@ protected:
   bool have_limits_ = false;
   bool attr_set_[10] = {false, false, false, false, false, false, false, false, false, false};
   bool use_fused_ = false; //!< K1 fused into K2 (decided once, at allocation)
+  bool lanes_attr_set_[12] = {};
+  int lanes_variant_ = envInt("NMPC_B200_BWD_LANES", 1); //!< 0: thread per instance, 1: G lanes, smem exchange, 2: shuffles
+  int lanes_tiles_per_cta_ = envInt("NMPC_B200_BWD_LANES_TPC", 1); //!< 32-instance tiles per CTA
+  int lanes_max_batch_ = envInt("NMPC_B200_BWD_LANES_MAXB", 16384);
   bool limits_vary_ = false; //!< the limits differ between horizon steps
   bool timing_ = false;
   std::vector<cudaEvent_t> events_;

@@ -676,8 +676,9 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
     for(int d = 0; d < NX * NX; d++) Vxx[d] = ws.vterm[(size_t)(NX + d) * Bp + b];
   }
 
-  dV0 = S(0);
-  dV1 = S(0);
+  // accumulated locally and handed back only when this instance needed the sweep: an instance that is merely waiting
+  // for its tile mates' lambda retry keeps the dV / k_rel_norm of its own successful sweep
+  S dV0_acc = S(0), dV1_acc = S(0);
   // max_i |k_i| / (|u_i| + 1) is tracked as a (numerator, denominator) pair and divided once
   S krn_num = S(0), krn_den = S(1);
 
@@ -941,8 +942,8 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
         s0 += k[a] * Qu[a];
         s1 += k[a] * Quuk[a];
       }
-      dV0 += s0;
-      dV1 += S(0.5) * s1;
+      dV0_acc += s0;
+      dV1_acc += S(0.5) * s1;
     }
     // KtQuu = K^T Quu (NX x NU)
     S KtQuu[NX * NU];
@@ -1029,7 +1030,12 @@ __device__ __forceinline__ bool backwardSweep(const M & model,
       u_nxt[a] = u_nx2[a];
     }
   }
-  k_rel_norm = krn_num / krn_den;
+  if(work)
+  {
+    dV0 = dV0_acc;
+    dV1 = dV1_acc;
+    k_rel_norm = krn_num / krn_den;
+  }
   return ok;
 }
 
