@@ -24,6 +24,7 @@
 #include "ddp_backward_fused.cuh"
 #include "ddp_backward_lanes.cuh"
 #include "ddp_forward_phased.cuh"
+#include "ddp_forward_split.cuh"
 #include "ddp_mpc.cuh"
 #include "registry.h"
 
@@ -818,6 +819,21 @@ protected:
   {
     using O = FwdOperands<NX, NU>;
     ensureFanout();
+    if(fwd_split_ != 0)
+    {
+      // one 32-instance tile per CTA: rollout warp + cost warp + loader warp (ddp_forward_split.cuh)
+      using SL = SplitLayout<M>;
+      const size_t smem = sizeof(S) * (SL::inElems(kTile) + SL::outElems(kTile))
+                          + sizeof(unsigned long long) * 2 * (kSplitIn + kSplitOut) + 16;
+      bool & attr_set = lanes_attr_set_[10];
+      if(!attr_set)
+      {
+        NMPC_CUDA_CHECK(cudaFuncSetAttribute(forward_first_split_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      launchPdl(forward_first_split_kernel<M>, dim3((B + kTile - 1) / kTile), dim3(96), smem, st, model_, ws_, prm_, fan_, iter);
+    }
+    else
     {
       // one 32-instance tile per CTA (compute warp + loader warp): 4096 instances cover 128 SMs
       const size_t smem = sizeof(S) * (size_t)kFirstDepth * O::SIZE * kTile + sizeof(unsigned long long) * 2 * kFirstDepth + 16;
@@ -829,6 +845,22 @@ protected:
       }
       launchPdl(forward_first_kernel<M>, dim3((B + kTile - 1) / kTile), dim3(64), smem, st, model_, ws_, prm_, fan_, iter);
     }
+    if(fwd_split_ != 0)
+    {
+      using SL = SplitLayout<M>;
+      constexpr int ipc = kFanWarps * (32 / kFanLanes); // listed instances per CTA
+      const size_t smem = sizeof(S) * ((size_t)kSplitIn * kSPS * ipc * O::SIZE + (size_t)kFanWarps * SL::outElems(kTile))
+                          + sizeof(unsigned long long) * (2 * kSplitIn + 2 * kSplitOut * kFanWarps) + 16;
+      bool & attr_set = lanes_attr_set_[11];
+      if(!attr_set)
+      {
+        NMPC_CUDA_CHECK(cudaFuncSetAttribute(forward_fanout_split_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      const int grid = (B + ipc - 1) / ipc; // worst case: every instance listed
+      launchPdl(forward_fanout_split_kernel<M>, dim3(grid), dim3((2 * kFanWarps + 1) * 32), smem, st, model_, ws_, prm_, fan_, iter);
+    }
+    else
     {
       constexpr int ipc = kFanWarps * (32 / kFanLanes); // listed instances per CTA
       const size_t smem = sizeof(S) * (size_t)kFanDepth * ipc * O::SIZE + sizeof(unsigned long long) * 2 * kFanDepth + 16;
@@ -1040,6 +1072,7 @@ protected:
   bool lanes_attr_set_[12] = {};
   int lanes_variant_ = envInt("NMPC_B200_BWD_LANES", 1); //!< 0: thread per instance, 1: G lanes, smem exchange, 2: shuffles
   int lanes_tiles_per_cta_ = envInt("NMPC_B200_BWD_LANES_TPC", 1); //!< 32-instance tiles per CTA
+  int fwd_split_ = envInt("NMPC_B200_FWD_SPLIT", 1); //!< phase 1 of the line search with rollout / cost / loader warps
   int lanes_max_batch_ = envInt("NMPC_B200_BWD_LANES_MAXB", 16384);
   bool limits_vary_ = false; //!< the limits differ between horizon steps
   bool timing_ = false;

@@ -1,0 +1,562 @@
+/* nmpc_b200 -- forwardPass() split over three warp roles (procOnce() Steps 3-4, DDPSolver.hpp:234-339, :537-560).
+ *
+ * One rollout is a dependent chain of N steps, and at a few thousand instances nothing else is in flight on the SM, so
+ * the line search costs (instructions on the chain) x (a lone warp's ~3.5 cycles per instruction).  In
+ * ddp_forward_phased.cuh the compute warp carries the whole step: u' = u + alpha k + K (x' - x), runningCost, stateEq,
+ * the stores of the candidate and their address arithmetic (~190 instructions, 660 cycles per step).  Here a step is
+ * split by what is ON the chain:
+ *
+ *   loader warp    streams {x_i, u_i, k_i, K_i} of the current trajectory into a shared-memory ring (cp.async)
+ *   ROLLOUT warp   u'_i, then x'_{i+1} = stateEq(t_i, x'_i, u'_i); publishes (x'_i, u'_i) to a second ring     [chain]
+ *   COST warp      runningCost(t_i, x'_i, u'_i), the sum, and every global store of the candidate       [off the chain]
+ *
+ * A ring stage holds kSPS = 2 steps, so the rollout warp passes its mbarriers once per two steps and the two steps
+ * form one basic block: with a branch-free functor (models/cartpole.h: sincos and reciprocal without slow-path
+ * branches) the compiler can start step i+1's trigonometry -- theta_{i+1} = theta_i + dt omega_i needs no input --
+ * under step i's reciprocal chain.  Arithmetic and summation order are those of forwardRollout (ddp_kernels.cuh):
+ * the same costs and trajectories bit for bit.
+ */
+#pragma once
+
+#include "ddp_forward_phased.cuh"
+
+namespace nmpc_b200
+{
+namespace ddp
+{
+constexpr int kSPS = 2; //!< steps per ring stage
+constexpr int kSplitIn = 4; //!< stages of the loader -> rollout ring
+constexpr int kSplitOut = 4; //!< stages of the rollout -> cost ring
+
+template<class M>
+struct SplitLayout
+{
+  using S = typename M::Scalar;
+  using O = FwdOperands<M::NX, M::NU>;
+  static constexpr int OUT = M::NX + M::NU; //!< (x'_i, u'_i)
+  /** Per group of `cols` ring columns (one column per rollout lane). */
+  static constexpr size_t inElems(int cols)
+  {
+    return (size_t)kSplitIn * kSPS * O::SIZE * cols;
+  }
+  static constexpr size_t outElems(int cols)
+  {
+    return (size_t)kSplitOut * kSPS * OUT * cols;
+  }
+};
+
+/** Rollout role.  Operand e of step slot q of in-stage st is in_ring[(st * kSPS + q) * IN_STAGE + in_off + e * IN_ES];
+    this lane's out column is out_col (element r of slot q of out-stage so at out_col[((so * kSPS + q) * OUT + r) * 32]).
+    Every lane of the warp runs the loop. */
+template<class M, int IN_STAGE, int IN_ES>
+__device__ __forceinline__ void splitRollout(const M & model,
+                                             typename M::Scalar t0,
+                                             int N,
+                                             typename M::Scalar alpha,
+                                             Matrix<typename M::Scalar, M::NX, 1> x,
+                                             const typename M::Scalar * in_ring,
+                                             int in_off,
+                                             unsigned long long * in_full,
+                                             unsigned long long * in_empty,
+                                             typename M::Scalar * out_col,
+                                             unsigned long long * out_full,
+                                             unsigned long long * out_empty)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  using O = FwdOperands<NX, NU>;
+  constexpr int OUT = NX + NU;
+  const S dt = model.dt();
+
+  auto step = [&](const S * op, S * oc, S t) {
+    S xr[NX], ur[NU], kr[NU], Kr[NU * NX];
+#pragma unroll
+    for(int d = 0; d < NX; d++) xr[d] = op[(size_t)(O::X + d) * IN_ES];
+#pragma unroll
+    for(int d = 0; d < NU; d++) ur[d] = op[(size_t)(O::U + d) * IN_ES];
+#pragma unroll
+    for(int d = 0; d < NU; d++) kr[d] = op[(size_t)(O::KFF + d) * IN_ES];
+#pragma unroll
+    for(int d = 0; d < NU * NX; d++) Kr[d] = op[(size_t)(O::KFB + d) * IN_ES];
+    Matrix<S, NU, 1> u;
+#pragma unroll
+    for(int c = 0; c < NU; c++)
+    {
+      S acc = S(0);
+#pragma unroll
+      for(int j = 0; j < NX; j++) acc += Kr[c + j * NU] * (x[j] - xr[j]);
+      u[c] = (ur[c] + alpha * kr[c]) + acc; // u' = u + alpha k + K (x' - x)   (:545-546)
+    }
+#pragma unroll
+    for(int d = 0; d < NX; d++) oc[(size_t)d * kTile] = x[d];
+#pragma unroll
+    for(int d = 0; d < NU; d++) oc[(size_t)(NX + d) * kTile] = u[d];
+    x = model.stateEq(t, x, u);
+  };
+
+  const int n_pairs = N / kSPS;
+  S fi = S(0); // == S(i) exactly
+  int g = 0;
+  for(; g < n_pairs; g++, fi += S(kSPS))
+  {
+    const int st = g % kSplitIn, so = g % kSplitOut;
+    mbarWait(&in_full[st], (unsigned)(g / kSplitIn) & 1u);
+    if(g >= kSplitOut) mbarWait(&out_empty[so], (unsigned)((g / kSplitOut) - 1) & 1u);
+    const S * op = in_ring + (size_t)st * kSPS * IN_STAGE + in_off;
+    S * oc = out_col + (size_t)so * kSPS * OUT * kTile;
+#pragma unroll
+    for(int q = 0; q < kSPS; q++) step(op + (size_t)q * IN_STAGE, oc + (size_t)q * OUT * kTile, t0 + (fi + S(q)) * dt);
+    mbarArrive(&in_empty[st]);
+    mbarArrive(&out_full[so]);
+  }
+  // tail: the odd last step (if any) and the terminal state share one out-stage; otherwise the terminal state alone
+  {
+    const int so = g % kSplitOut;
+    if(g >= kSplitOut) mbarWait(&out_empty[so], (unsigned)((g / kSplitOut) - 1) & 1u);
+    S * oc = out_col + (size_t)so * kSPS * OUT * kTile;
+    int q = 0;
+    if(N % kSPS != 0)
+    {
+      const int st = g % kSplitIn;
+      mbarWait(&in_full[st], (unsigned)(g / kSplitIn) & 1u);
+      step(in_ring + (size_t)st * kSPS * IN_STAGE + in_off, oc, t0 + fi * dt);
+      mbarArrive(&in_empty[st]);
+      q = 1;
+    }
+#pragma unroll
+    for(int d = 0; d < NX; d++) oc[((size_t)q * OUT + d) * kTile] = x[d];
+    mbarArrive(&out_full[so]);
+  }
+}
+
+/** Cost role: running / terminal costs of the candidate published by the rollout role, their sum (in the order of
+    forwardRollout), and -- for `store` lanes -- the candidate trajectory written to dst. */
+template<class M>
+__device__ __forceinline__ typename M::Scalar splitCost(const M & model,
+                                                        typename M::Scalar t0,
+                                                        int N,
+                                                        const typename M::Scalar * out_col,
+                                                        unsigned long long * out_full,
+                                                        unsigned long long * out_empty,
+                                                        bool store,
+                                                        const FwdDest<typename M::Scalar> & dst)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  constexpr int OUT = NX + NU;
+  const S dt = model.dt();
+  S * xs_ptr = dst.x + dst.col;
+  S * us_ptr = dst.u + dst.col;
+  S * cs_ptr = dst.c + dst.col;
+  const size_t Bd = dst.stride;
+  S csum = S(0);
+  S fi = S(0);
+  const int n_stages = (N + 1 + kSPS - 1) / kSPS;
+  for(int g = 0; g < n_stages; g++)
+  {
+    const int so = g % kSplitOut;
+    mbarWait(&out_full[so], (unsigned)(g / kSplitOut) & 1u);
+    const S * oc = out_col + (size_t)so * kSPS * OUT * kTile;
+    S xv[kSPS][NX], uv[kSPS][NU];
+#pragma unroll
+    for(int q = 0; q < kSPS; q++)
+    {
+#pragma unroll
+      for(int d = 0; d < NX; d++) xv[q][d] = oc[((size_t)q * OUT + d) * kTile];
+#pragma unroll
+      for(int d = 0; d < NU; d++) uv[q][d] = oc[((size_t)q * OUT + NX + d) * kTile];
+    }
+    mbarArrive(&out_empty[so]);
+#pragma unroll
+    for(int q = 0; q < kSPS; q++)
+    {
+      const int i = g * kSPS + q;
+      if(i > N) break;
+      Matrix<S, NX, 1> x;
+#pragma unroll
+      for(int d = 0; d < NX; d++) x[d] = xv[q][d];
+      S c;
+      if(i < N)
+      {
+        Matrix<S, NU, 1> u;
+#pragma unroll
+        for(int d = 0; d < NU; d++) u[d] = uv[q][d];
+        c = model.runningCost(t0 + fi * dt, x, u);
+        if(store)
+        {
+#pragma unroll
+          for(int d = 0; d < NU; d++) us_ptr[(size_t)d * Bd] = u[d];
+        }
+      }
+      else
+        c = model.terminalCost(t0 + fi * dt, x);
+      if(store)
+      {
+#pragma unroll
+        for(int d = 0; d < NX; d++) xs_ptr[(size_t)d * Bd] = x[d];
+        *cs_ptr = c;
+      }
+      csum += c;
+      xs_ptr += (size_t)NX * Bd;
+      us_ptr += (size_t)NU * Bd;
+      cs_ptr += Bd;
+      fi += S(1);
+    }
+  }
+  return csum;
+}
+
+/** Loader role for one 32-instance tile: lane l streams the operands of its own instance, kSPS steps per stage. */
+template<class M>
+__device__ __forceinline__ void splitLoadTile(const Workspace<typename M::Scalar> & ws,
+                                              int N,
+                                              int lane,
+                                              int b,
+                                              int sel,
+                                              typename M::Scalar * in_ring,
+                                              unsigned long long * in_full,
+                                              unsigned long long * in_empty)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  using O = FwdOperands<NX, NU>;
+  const size_t Bp = ws.Bp;
+  const S * row_ptr[O::SIZE];
+  long long row_stride[O::SIZE];
+#pragma unroll
+  for(int e = 0; e < O::SIZE; e++)
+  {
+    if(e < O::U)
+    {
+      row_ptr[e] = ws.x[sel] + (size_t)(e - O::X) * Bp + b;
+      row_stride[e] = (long long)NX * (long long)Bp;
+    }
+    else if(e < O::KFF)
+    {
+      row_ptr[e] = ws.u[sel] + (size_t)(e - O::U) * Bp + b;
+      row_stride[e] = (long long)NU * (long long)Bp;
+    }
+    else if(e < O::KFB)
+    {
+      row_ptr[e] = ws.kff + (size_t)(e - O::KFF) * Bp + b;
+      row_stride[e] = (long long)NU * (long long)Bp;
+    }
+    else
+    {
+      row_ptr[e] = ws.kfb + (size_t)(e - O::KFB) * Bp + b;
+      row_stride[e] = (long long)(NU * NX) * (long long)Bp;
+    }
+  }
+  const int n_fills = (N + kSPS - 1) / kSPS;
+  for(int f = 0; f < n_fills; f++)
+  {
+    const int st = f % kSplitIn;
+    if(f >= kSplitIn) mbarWait(&in_empty[st], (unsigned)((f / kSplitIn) - 1) & 1u);
+    S * dstp = in_ring + (size_t)st * kSPS * O::SIZE * kTile + lane;
+#pragma unroll
+    for(int q = 0; q < kSPS; q++)
+    {
+      const bool in_range = f * kSPS + q < N; // the slot past an odd horizon's last step is never read
+#pragma unroll
+      for(int e = 0; e < O::SIZE; e++)
+      {
+        if(in_range)
+        {
+          if constexpr(sizeof(S) == 8)
+            cpAsync8(dstp + ((size_t)q * O::SIZE + e) * kTile, row_ptr[e]);
+          else
+            cpAsync4(dstp + ((size_t)q * O::SIZE + e) * kTile, row_ptr[e]);
+        }
+        row_ptr[e] += row_stride[e];
+      }
+    }
+    cpAsyncArriveOn(&in_full[st]);
+  }
+}
+
+/** Phase 1 of the line search: alpha_list[0] for every running instance of a 32-instance tile.
+    Warp 0 rolls out, warp 1 evaluates costs / stores / decides, warp 2 loads. */
+template<class M>
+__global__ void __launch_bounds__(96) forward_first_split_kernel(const __grid_constant__ M model_in_constant_bank,
+                                                                  const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                                                  const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                                                  const __grid_constant__ FwdFanout<typename M::Scalar> fan,
+                                                                  int iter)
+{
+  pdlPrologue();
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX;
+  using SL = SplitLayout<M>;
+  using O = typename SL::O;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S * in_ring = reinterpret_cast<S *>(smem_raw);
+  S * out_ring = in_ring + SL::inElems(kTile);
+  unsigned long long * in_full = reinterpret_cast<unsigned long long *>(out_ring + SL::outElems(kTile));
+  unsigned long long * in_empty = in_full + kSplitIn;
+  unsigned long long * out_full = in_empty + kSplitIn;
+  unsigned long long * out_empty = out_full + kSplitOut;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if(threadIdx.x == 0)
+  {
+    for(int st = 0; st < kSplitIn; st++)
+    {
+      mbarInit(&in_full[st], 32);
+      mbarInit(&in_empty[st], 32);
+    }
+    for(int st = 0; st < kSplitOut; st++)
+    {
+      mbarInit(&out_full[st], 32);
+      mbarInit(&out_empty[st], 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  const int bg = blockIdx.x * kTile + lane;
+  const int b = (bg < ws.B) ? bg : (ws.B - 1);
+  const bool active = (bg < ws.B) && (ws.status[b] == 0);
+  // all three warps see the same 32 verdicts: uniform exit; the barrier also publishes the mbarrier initialisation
+  if(!__syncthreads_or(active)) return;
+  const int sel = ws.sel[b];
+  const int N = prm.N;
+
+  if(warp == 2)
+  {
+    splitLoadTile<M>(ws, N, lane, b, sel, in_ring, in_full, in_empty);
+    return;
+  }
+  const M model = model_in_constant_bank;
+  const S alpha = prm.alpha_list[0];
+  if(warp == 0)
+  {
+    Matrix<S, NX, 1> x;
+#pragma unroll
+    for(int d = 0; d < NX; d++) x[d] = ws.x[sel][(size_t)d * ws.Bp + b];
+    splitRollout<M, O::SIZE * kTile, kTile>(model, prm.t0, N, alpha, x, in_ring, lane, in_full, in_empty, out_ring + lane,
+                                            out_full, out_empty);
+    return;
+  }
+  const bool work = active && prm.n_alpha > 0;
+  const S cost_new = splitCost<M>(model, prm.t0, N, out_ring + lane, out_full, out_empty, work, candidateBuffer<S>(ws, sel, b));
+  if(!active) return;
+  const S cost_cur = ws.cost_sum[b];
+  S actual = S(0), expected = S(0), ratio = S(0);
+  bool success = false;
+  if(work) success = lineSearchTest<S>(prm, cost_cur, cost_new, alpha, ws.dV[b], ws.dV[(size_t)ws.Bp + b], actual,
+                                       expected, ratio);
+  if(success || prm.n_alpha <= 1)
+  {
+    lineSearchFinish<S>(ws, prm, b, iter, sel, success, work ? alpha : S(0), actual, expected, ratio, cost_cur,
+                        cost_new, work ? 1 : 0);
+    return;
+  }
+  const int slot = atomicAdd(fan.count, 1);
+  fan.list[slot] = b;
+}
+
+/** Phase 2 of the line search (see forward_fanout_kernel): candidates 1 .. n_alpha-1 of every listed instance at once,
+    16 lanes per listed instance, with the three roles above.  CTA = kFanWarps rollout warps + kFanWarps cost warps (warp
+    kFanWarps + w is the partner of warp w: same lane = same candidate) + one loader warp streaming the operands of the
+    CTA's eight instances (read as a broadcast by the lanes of a group). */
+template<class M>
+__global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
+    forward_fanout_split_kernel(const __grid_constant__ M model_in_constant_bank,
+                                const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                const __grid_constant__ FwdFanout<typename M::Scalar> fan,
+                                int iter)
+{
+  pdlPrologue();
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  using SL = SplitLayout<M>;
+  using O = typename SL::O;
+  constexpr int GA = kFanLanes;
+  constexpr int IPW = 32 / GA; // listed instances per rollout warp
+  constexpr int IPC = kFanWarps * IPW; // ... per CTA
+  constexpr int ROWS = IPC * O::SIZE; // in-ring rows of one step: [instance of the CTA][operand]
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr unsigned kGroupMask = (1u << GA) - 1u;
+  const int count = *fan.count;
+  const int cta_slot0 = blockIdx.x * IPC;
+  if(cta_slot0 >= count) return; // CTA-uniform
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S * in_ring = reinterpret_cast<S *>(smem_raw); // [kSplitIn][kSPS][ROWS]
+  S * out_ring = in_ring + (size_t)kSplitIn * kSPS * ROWS; // [kFanWarps][kSplitOut][kSPS][OUT][32]
+  unsigned long long * in_full = reinterpret_cast<unsigned long long *>(out_ring + (size_t)kFanWarps * SL::outElems(kTile));
+  unsigned long long * in_empty = in_full + kSplitIn;
+  unsigned long long * out_bars = in_empty + kSplitIn; // per pair: kSplitOut full, kSplitOut empty
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if(threadIdx.x == 0)
+  {
+    for(int st = 0; st < kSplitIn; st++)
+    {
+      mbarInit(&in_full[st], 32);
+      mbarInit(&in_empty[st], kFanWarps * 32);
+    }
+    for(int st = 0; st < 2 * kSplitOut * kFanWarps; st++) mbarInit(&out_bars[st], 32);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const size_t Bp = ws.Bp;
+  const int N = prm.N;
+
+  if(warp == 2 * kFanWarps)
+  {
+    // loader: lane l streams in-ring rows l, l + 32, ... of every step; row = (instance of the CTA) * O::SIZE + operand
+    constexpr int RPL = (ROWS + 31) / 32;
+    const S * row_ptr[RPL];
+    long long row_stride[RPL];
+#pragma unroll
+    for(int q = 0; q < RPL; q++)
+    {
+      const int row = q * 32 + lane;
+      const int inst = (row < ROWS) ? row / O::SIZE : 0;
+      const int e = (row < ROWS) ? row % O::SIZE : 0;
+      const int slot = cta_slot0 + inst;
+      const int b = fan.list[slot < count ? slot : cta_slot0]; // surplus slots repeat a valid instance
+      const int sel = ws.sel[b];
+      if(e < O::U)
+      {
+        row_ptr[q] = ws.x[sel] + (size_t)(e - O::X) * Bp + b;
+        row_stride[q] = (long long)NX * (long long)Bp;
+      }
+      else if(e < O::KFF)
+      {
+        row_ptr[q] = ws.u[sel] + (size_t)(e - O::U) * Bp + b;
+        row_stride[q] = (long long)NU * (long long)Bp;
+      }
+      else if(e < O::KFB)
+      {
+        row_ptr[q] = ws.kff + (size_t)(e - O::KFF) * Bp + b;
+        row_stride[q] = (long long)NU * (long long)Bp;
+      }
+      else
+      {
+        row_ptr[q] = ws.kfb + (size_t)(e - O::KFB) * Bp + b;
+        row_stride[q] = (long long)(NU * NX) * (long long)Bp;
+      }
+    }
+    const int n_fills = (N + kSPS - 1) / kSPS;
+    for(int f = 0; f < n_fills; f++)
+    {
+      const int st = f % kSplitIn;
+      if(f >= kSplitIn) mbarWait(&in_empty[st], (unsigned)((f / kSplitIn) - 1) & 1u);
+#pragma unroll
+      for(int sq = 0; sq < kSPS; sq++)
+      {
+        const bool in_range = f * kSPS + sq < N;
+#pragma unroll
+        for(int q = 0; q < RPL; q++)
+        {
+          const int row = q * 32 + lane;
+          if(row < ROWS && in_range)
+          {
+            if constexpr(sizeof(S) == 8)
+              cpAsync8(in_ring + ((size_t)st * kSPS + sq) * ROWS + row, row_ptr[q]);
+            else
+              cpAsync4(in_ring + ((size_t)st * kSPS + sq) * ROWS + row, row_ptr[q]);
+          }
+          row_ptr[q] += row_stride[q];
+        }
+      }
+      cpAsyncArriveOn(&in_full[st]);
+    }
+    return;
+  }
+
+  const M model = model_in_constant_bank;
+  const int pair = warp % kFanWarps;
+  const int g = lane / GA;
+  const int a = lane % GA;
+  const int inst = pair * IPW + g; // instance of the CTA
+  const int slot = cta_slot0 + inst;
+  const bool valid = slot < count;
+  const int b = fan.list[valid ? slot : cta_slot0];
+  const int sel = ws.sel[b];
+  const int rem = prm.n_alpha - 1;
+  const bool work = valid && (a < rem);
+  const S my_alpha = prm.alpha_list[work ? (1 + a) : 0];
+  S * out_col = out_ring + (size_t)pair * SL::outElems(kTile) + lane;
+  unsigned long long * out_full = out_bars + (size_t)pair * 2 * kSplitOut;
+  unsigned long long * out_empty = out_full + kSplitOut;
+
+  if(warp < kFanWarps)
+  {
+    Matrix<S, NX, 1> x;
+#pragma unroll
+    for(int d = 0; d < NX; d++) x[d] = ws.x[sel][(size_t)d * Bp + b];
+    splitRollout<M, ROWS, 1>(model, prm.t0, N, my_alpha, x, in_ring, inst * O::SIZE, in_full, in_empty, out_col, out_full,
+                             out_empty);
+    return;
+  }
+
+  // ------------------------------------------------------------------ cost warps
+  const size_t item = (size_t)slot * GA + a; // scratch column of this candidate
+  const FwdDest<S> dst{fan.sx, fan.su, fan.sc, fan.items, item};
+  const S my_cost = splitCost<M>(model, prm.t0, N, out_col, out_full, out_empty, work, dst);
+
+  const S cost_cur = ws.cost_sum[b];
+  S my_actual = S(0), my_expected = S(0), my_ratio = S(0);
+  bool ok = false;
+  if(work)
+    ok = lineSearchTest<S>(prm, cost_cur, my_cost, my_alpha, ws.dV[b], ws.dV[(size_t)ws.Bp + b], my_actual, my_expected,
+                           my_ratio);
+  const unsigned ok_ballot = __ballot_sync(kFull, ok);
+  const unsigned gm = (ok_ballot >> (g * GA)) & kGroupMask;
+  const int pick = (gm != 0) ? (__ffs(gm) - 1) : (rem - 1); // first success, else the last candidate tried
+  const int src_lane = g * GA + pick;
+  const S r_actual = __shfl_sync(kFull, my_actual, src_lane);
+  const S r_expected = __shfl_sync(kFull, my_expected, src_lane);
+  const S r_ratio = __shfl_sync(kFull, my_ratio, src_lane);
+  const S r_cost = __shfl_sync(kFull, my_cost, src_lane);
+  const S r_alpha = __shfl_sync(kFull, my_alpha, src_lane);
+  const bool success = valid && (gm != 0);
+  if(valid && a == 0)
+  {
+    fan.commit_item[slot] = success ? (int)((size_t)slot * GA + pick) : -1;
+    lineSearchFinish<S>(ws, prm, b, iter, sel, success, r_alpha, r_actual, r_expected, r_ratio, cost_cur, r_cost,
+                        success ? (2 + pick) : prm.n_alpha);
+  }
+  // Phase 3, fused: the group copies its winner's scratch trajectory into the instance's other buffer (which
+  // lineSearchFinish has just made the current one).  The winner lane's global stores are ordered before the
+  // group's loads by the warp barrier.
+  __syncwarp();
+  if(success)
+  {
+    const size_t win = (size_t)slot * GA + pick;
+    const int rows_x = (N + 1) * NX, rows_u = N * NU, rows_c = N + 1;
+    S * __restrict__ dx = ws.x[sel ^ 1];
+    S * __restrict__ du = ws.u[sel ^ 1];
+    S * __restrict__ dc = ws.cost[sel ^ 1];
+    const int rows = rows_x + rows_u + rows_c;
+    auto src = [&](int r) -> const S * {
+      return (r < rows_x) ? fan.sx + (size_t)r * fan.items + win
+                          : (r < rows_x + rows_u) ? fan.su + (size_t)(r - rows_x) * fan.items + win
+                                                  : fan.sc + (size_t)(r - rows_x - rows_u) * fan.items + win;
+    };
+    auto dstp = [&](int r) -> S * {
+      return (r < rows_x) ? dx + (size_t)r * Bp + b
+                          : (r < rows_x + rows_u) ? du + (size_t)(r - rows_x) * Bp + b
+                                                  : dc + (size_t)(r - rows_x - rows_u) * Bp + b;
+    };
+    for(int r0 = a; r0 < rows; r0 += GA * 8)
+    {
+      S v[8];
+#pragma unroll
+      for(int q = 0; q < 8; q++)
+      {
+        const int r = r0 + q * GA;
+        if(r < rows) v[q] = *src(r);
+      }
+#pragma unroll
+      for(int q = 0; q < 8; q++)
+      {
+        const int r = r0 + q * GA;
+        if(r < rows) *dstp(r) = v[q];
+      }
+    }
+  }
+}
+} // namespace ddp
+} // namespace nmpc_b200
