@@ -34,6 +34,16 @@ namespace nmpc_b200
 namespace ddp
 {
 constexpr int kLaneDepth = 4; //!< ring stages between the producer warps and the consumer warps
+/** Elements between two pair-rows of a staged tile: 32 instances x 2 elements, plus one pair of padding.  Lane j of a
+    group reads ITS column's rows (rows 2 j + q for n_x = 4): with an unpadded 512-byte row the four lanes of a group
+    hit the same banks (ncu: 2.7 M of the 6.3 M shared-load wavefronts of a sweep were bank conflicts); with 528 bytes
+    the eight lanes of a quarter-warp access touch eight different 16-byte bank groups. */
+constexpr int kLaneRow = 2 * kTile + 2;
+/** Elements of one ring stage for a tile of SIZE elements per instance. */
+constexpr size_t laneStageElems(int size)
+{
+  return (size_t)(size / 2) * kLaneRow;
+}
 
 constexpr int evenUp(int v)
 {
@@ -73,7 +83,7 @@ struct LaneTile
 template<class S>
 __device__ __forceinline__ S tileElem(const S * tl, int e)
 {
-  return tl[(size_t)(e >> 1) * (2 * kTile) + (e & 1)];
+  return tl[(size_t)(e >> 1) * kLaneRow + (e & 1)];
 }
 
 /** CNT consecutive elements from e0; PAIRS: e0 is even, so pairs are read with one 2-element access. */
@@ -86,7 +96,7 @@ __device__ __forceinline__ void tileLoad(const S * tl, int e0, S * out)
 #pragma unroll
     for(int q = 0; q < CNT / 2; q++)
     {
-      const V v = *reinterpret_cast<const V *>(tl + (size_t)((e0 >> 1) + q) * (2 * kTile));
+      const V v = *reinterpret_cast<const V *>(tl + (size_t)((e0 >> 1) + q) * kLaneRow);
       out[2 * q] = v.x;
       out[2 * q + 1] = v.y;
     }
@@ -164,12 +174,17 @@ struct LaneLayout
   using T = LaneTile<NX, NU>;
   static constexpr int X1 = 2 * NU; //!< exchange 1 per lane: Qux(:,j), K(:,j)
   static constexpr int X2 = NX + 1; //!< exchange 2 per lane: Vxx'(:,j), Vx'(j)
-  // scratch strides in elements: a multiple of 16 elements + 2, so that the groups of a warp hit different banks
-  static constexpr int X1S = ((G * evenUp(X1) + 15) / 16) * 16 + 2;
-  static constexpr int X2S = ((G * evenUp(X2) + 15) / 16) * 16 + 2;
+  // scratch strides in elements: 8 modulo 16 (64 bytes modulo 128 for fp64), so that the two instances a quarter-warp
+  // access covers land in different halves of the banks, for the lanes' writes and for the broadcast reads alike
+  static constexpr int strideFor(int n)
+  {
+    return n <= 8 ? 8 : ((n - 8 + 15) / 16) * 16 + 8;
+  }
+  static constexpr int X1S = strideFor(G * evenUp(X1));
+  static constexpr int X2S = strideFor(G * evenUp(X2));
   static constexpr size_t ringElems()
   {
-    return (size_t)kLaneDepth * T::SIZE * kTile;
+    return (size_t)kLaneDepth * laneStageElems(T::SIZE);
   }
   static constexpr size_t scratchElems()
   {
@@ -190,9 +205,9 @@ __device__ __forceinline__ void produceSweepLanes(const M & model_in_constant_ba
                                                   int b,
                                                   int t,
                                                   int p,
-                                                  const typename M::Scalar * __restrict__ xs,
-                                                  const typename M::Scalar * __restrict__ us,
-                                                  typename M::Scalar * __restrict__ ring,
+                                                  const typename M::Scalar * xs,
+                                                  const typename M::Scalar * us,
+                                                  typename M::Scalar * ring,
                                                   unsigned long long * full,
                                                   unsigned long long * empty,
                                                   unsigned fill_base)
@@ -267,14 +282,14 @@ __device__ __forceinline__ void produceSweepLanes(const M & model_in_constant_ba
     const unsigned fg = fill_base + (unsigned)f;
     const unsigned st = fg % kLaneDepth;
     if(fg >= (unsigned)kLaneDepth) mbarWait(&empty[st], ((fg / kLaneDepth) - 1u) & 1u); // the consumers are done with it
-    S * tl = ring + (size_t)st * T::SIZE * kTile + 2 * t;
+    S * tl = ring + (size_t)st * laneStageElems(T::SIZE) + 2 * t;
 #pragma unroll
     for(int q = 0; q < T::SIZE / 2; q++)
     {
       V w;
       w.x = v[2 * q];
       w.y = v[2 * q + 1];
-      *reinterpret_cast<V *>(tl + (size_t)q * (2 * kTile)) = w;
+      *reinterpret_cast<V *>(tl + (size_t)q * kLaneRow) = w;
     }
     mbarArrive(&full[st]); // release: this lane's column of the tile
 
@@ -352,7 +367,7 @@ __device__ __forceinline__ bool laneSweep(const M & model,
                                           int lane,
                                           int j,
                                           int jj,
-                                          const typename M::Scalar * __restrict__ xs,
+                                          const typename M::Scalar * xs,
                                           const typename M::Scalar * ring,
                                           typename M::Scalar * x1,
                                           typename M::Scalar * x2,
@@ -402,7 +417,7 @@ __device__ __forceinline__ bool laneSweep(const M & model,
   {
     const unsigned st = fill % kLaneDepth;
     mbarWait(&full[st], (fill / kLaneDepth) & 1u);
-    loadLaneTile<M>(tl0 + (size_t)st * TL::SIZE * kTile, jj, T);
+    loadLaneTile<M>(tl0 + (size_t)st * laneStageElems(TL::SIZE), jj, T);
     mbarArrive(&empty[st]);
     fill++;
   }
@@ -618,7 +633,7 @@ __device__ __forceinline__ bool laneSweep(const M & model,
     if(i > 0)
     {
       if(!next_ready) mbarWait(&full[stn], parn);
-      loadLaneTile<M>(tl0 + (size_t)stn * TL::SIZE * kTile, jj, T);
+      loadLaneTile<M>(tl0 + (size_t)stn * laneStageElems(TL::SIZE), jj, T);
       mbarArrive(&empty[stn]);
       fill++;
     }
@@ -727,90 +742,105 @@ __device__ __forceinline__ bool laneSweep(const M & model,
   return ok;
 }
 
-/** procOnce() Steps 1-2.  A CTA holds TPC independent 32-instance tiles (each with its own ring, scratch and
-    mbarriers); per tile, warps 0 .. G-1 run the sweep (G lanes per instance) and warps G .. G+P-1 linearise.  With
-    TPC = 2 every warp scheduler of the SM has two consumer warps to alternate between. */
-template<class M, bool CONSTRAINED, int P, class XCH, int TPC>
-__global__ void __launch_bounds__((LaneLayout<M>::CW + P) * 32 * TPC)
-    backward_lanes_kernel(const __grid_constant__ M model_in_constant_bank,
-                          const __grid_constant__ Workspace<typename M::Scalar> ws,
-                          const __grid_constant__ SolverParams<typename M::Scalar> prm,
-                          int iter)
+/** Shared-memory carve-up of one tile's backward pass. */
+template<class M>
+struct LaneSmem
 {
-  pdlPrologue();
   using S = typename M::Scalar;
-  constexpr int NX = M::NX;
-  using LL = LaneLayout<M>;
-  constexpr int G = LL::G, IPW = LL::IPW, CW = LL::CW;
-  static_assert(NX <= G, "one column per lane");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int sub = (threadIdx.x >> 5) / (CW + P); // tile of the CTA
-  const int warp = (threadIdx.x >> 5) % (CW + P); // warp of the tile
-  const int lane = threadIdx.x & 31;
-  S * ring = reinterpret_cast<S *>(smem_raw + (size_t)sub * LL::bytes());
-  S * scratch = ring + LL::ringElems();
-  unsigned long long * full = reinterpret_cast<unsigned long long *>(scratch + LL::scratchElems());
-  unsigned long long * empty = full + kLaneDepth;
-  if(warp == 0 && lane == 0)
+  S * ring;
+  S * scratch;
+  unsigned long long * full;
+  unsigned long long * empty;
+  __device__ __forceinline__ explicit LaneSmem(unsigned char * base)
+  {
+    using LL = LaneLayout<M>;
+    ring = reinterpret_cast<S *>(base);
+    scratch = ring + LL::ringElems();
+    full = reinterpret_cast<unsigned long long *>(scratch + LL::scratchElems());
+    empty = full + kLaneDepth;
+  }
+  /** One thread, before a CTA barrier. */
+  __device__ __forceinline__ void initBarriers() const
   {
     for(int st = 0; st < kLaneDepth; st++)
     {
       mbarInit(&full[st], 32);
-      mbarInit(&empty[st], CW * 32);
+      mbarInit(&empty[st], LaneLayout<M>::CW * 32);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    if(blockIdx.x == 0 && sub == 0) *ws.fan_count = 0; // the previous iteration's line-search work list is consumed
   }
+};
 
-  const bool producer = warp >= CW;
-  const int t = producer ? lane : (warp * IPW + lane / G); // instance of the tile
-  const int j = lane % G; // consumer: this lane's column
-  const int jj = (j < NX) ? j : (NX - 1); // idle lanes (n_x < G) shadow the last column and never store
-  // ws.Bp is a multiple of 128 (four tiles): padded lanes read valid memory, never write
-  const int b = (blockIdx.x * TPC + sub) * kTile + t;
-  const bool live = (b < ws.B) && (ws.status[b < ws.B ? b : 0] == 0);
-  // CTA-uniform exit; the barrier also publishes the mbarrier initialisation
-  if(!__syncthreads_or(live)) return;
-
-  const int sel = live ? ws.sel[b] : 0;
-  const S * us = ws.u[sel];
-  const S * xs = ws.x[sel];
-  const int N = prm.N;
-
-  if(producer)
+/** Producer warp p of P: linearises sweep after sweep until the consumers' vote says no instance of the tile needs
+    another one.  `fill` is the ring's running tile count (continues across calls). */
+template<class M, int P>
+__device__ __forceinline__ void laneBackwardProducer(const M & model_in_constant_bank,
+                                                     const Workspace<typename M::Scalar> & ws,
+                                                     const SolverParams<typename M::Scalar> & prm,
+                                                     const LaneSmem<M> & sm,
+                                                     int b,
+                                                     int t,
+                                                     int p,
+                                                     const typename M::Scalar * xs,
+                                                     const typename M::Scalar * us,
+                                                     unsigned & fill)
+{
+  while(true)
   {
-    unsigned fill_base = 0;
-    while(true)
-    {
-      produceSweepLanes<M, P>(model_in_constant_bank, ws, prm, b, t, warp - CW, xs, us, ring, full, empty, fill_base);
-      fill_base += (unsigned)N;
-      if(!__syncthreads_or(0)) break; // the consumers decide whether lambda must grow and the sweep be repeated
-    }
-    return;
+    produceSweepLanes<M, P>(model_in_constant_bank, ws, prm, b, t, p, xs, us, sm.ring, sm.full, sm.empty, fill);
+    fill += (unsigned)prm.N;
+    if(!__syncthreads_or(0)) break; // the consumers decide whether lambda must grow and the sweep be repeated
   }
+}
 
-  // -------------------------------------------------------------------- consumers
-  const M model = model_in_constant_bank;
-  // two scratch arrays, each with an instance stride of 16 m + 2 elements: the 8 groups of a warp reading the same
-  // offset of their own instance with 16-byte accesses touch 32 different banks
-  S * x1 = scratch + (size_t)t * LL::X1S;
-  S * x2 = scratch + (size_t)kTile * LL::X1S + (size_t)t * LL::X2S;
+/** A warp of the CTA without a role in the backward pass: takes part in the votes. */
+__device__ __forceinline__ void laneBackwardIdle(int N, unsigned & fill)
+{
+  while(true)
+  {
+    fill += (unsigned)N;
+    if(!__syncthreads_or(0)) break;
+  }
+}
+
+/** Consumer lane (instance t of the tile, column j): procOnce() Step 2 (:188-231) -- sweeps with growing lambda until
+    the factorisation succeeds, then the small-gradient termination test and the hand-over to the line search. */
+template<class M, bool CONSTRAINED, class XCH>
+__device__ __forceinline__ void laneBackwardConsumer(const M & model,
+                                                     const Workspace<typename M::Scalar> & ws,
+                                                     const SolverParams<typename M::Scalar> & prm,
+                                                     const LaneSmem<M> & sm,
+                                                     int b,
+                                                     int t,
+                                                     int lane,
+                                                     bool live,
+                                                     const typename M::Scalar * xs,
+                                                     int iter,
+                                                     unsigned & fill)
+{
+  using S = typename M::Scalar;
+  using LL = LaneLayout<M>;
+  constexpr int NX = M::NX, G = LL::G;
+  const int j = lane % G; // this lane's column
+  const int jj = (j < NX) ? j : (NX - 1); // idle lanes (n_x < G) shadow the last column and never store
+  // two scratch arrays (strides: LaneLayout::strideFor)
+  S * x1 = sm.scratch + (size_t)t * LL::X1S;
+  S * x2 = sm.scratch + (size_t)kTile * LL::X1S + (size_t)t * LL::X2S;
   S lambda = live ? ws.lambda[b] : S(0);
   S dlambda = live ? ws.dlambda[b] : S(0);
   int n_bwd = live ? ws.n_bwd[b] : 0;
   S dV0 = S(0), dV1 = S(0), k_rel_norm = S(0);
   bool need = live;
   bool failed = false;
-  unsigned fill = 0;
 
   while(true)
   {
     if(need) n_bwd++;
-    const bool ok = (prm.reg_type == 2)
-                        ? laneSweep<M, CONSTRAINED, true, XCH>(model, ws, prm, b, t, lane, j, jj, xs, ring, x1, x2, full, empty,
-                                                               fill, need, lambda, dV0, dV1, k_rel_norm)
-                        : laneSweep<M, CONSTRAINED, false, XCH>(model, ws, prm, b, t, lane, j, jj, xs, ring, x1, x2, full, empty,
-                                                                fill, need, lambda, dV0, dV1, k_rel_norm);
+    const bool ok = (prm.reg_type == 2) ? laneSweep<M, CONSTRAINED, true, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1, x2,
+                                                                               sm.full, sm.empty, fill, need, lambda, dV0, dV1,
+                                                                               k_rel_norm)
+                                        : laneSweep<M, CONSTRAINED, false, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1,
+                                                                                x2, sm.full, sm.empty, fill, need, lambda, dV0, dV1,
+                                                                                k_rel_norm);
     if(need)
     {
       if(ok)
@@ -855,6 +885,54 @@ __global__ void __launch_bounds__((LaneLayout<M>::CW + P) * 32 * TPC)
   }
   // hand k_rel_norm to the forward kernel through the trace row
   ws.trace[((size_t)iter * kTraceFields + 5) * ws.Bp + b] = k_rel_norm;
+}
+
+/** procOnce() Steps 1-2 as a kernel of its own.  A CTA holds TPC independent 32-instance tiles (each with its own ring,
+    scratch and mbarriers); per tile, warps 0 .. G-1 run the sweep (G lanes per instance) and warps G .. G+P-1
+    linearise. */
+template<class M, bool CONSTRAINED, int P, class XCH, int TPC>
+__global__ void __launch_bounds__((LaneLayout<M>::CW + P) * 32 * TPC)
+    backward_lanes_kernel(const __grid_constant__ M model_in_constant_bank,
+                          const __grid_constant__ Workspace<typename M::Scalar> ws,
+                          const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                          int iter)
+{
+  pdlPrologue();
+  using S = typename M::Scalar;
+  using LL = LaneLayout<M>;
+  constexpr int G = LL::G, IPW = LL::IPW, CW = LL::CW;
+  static_assert(M::NX <= G, "one column per lane");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int sub = (threadIdx.x >> 5) / (CW + P); // tile of the CTA
+  const int warp = (threadIdx.x >> 5) % (CW + P); // warp of the tile
+  const int lane = threadIdx.x & 31;
+  const LaneSmem<M> sm(smem_raw + (size_t)sub * LL::bytes());
+  if(warp == 0 && lane == 0)
+  {
+    sm.initBarriers();
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    if(blockIdx.x == 0 && sub == 0) *ws.fan_count = 0; // the previous iteration's line-search work list is consumed
+  }
+
+  const bool producer = warp >= CW;
+  const int t = producer ? lane : (warp * IPW + lane / G); // instance of the tile
+  // ws.Bp is a multiple of 128 (four tiles): padded lanes read valid memory, never write
+  const int b = (blockIdx.x * TPC + sub) * kTile + t;
+  const bool live = (b < ws.B) && (ws.status[b < ws.B ? b : 0] == 0);
+  // CTA-uniform exit; the barrier also publishes the mbarrier initialisation
+  if(!__syncthreads_or(live)) return;
+
+  const int sel = live ? ws.sel[b] : 0;
+  const S * us = ws.u[sel];
+  const S * xs = ws.x[sel];
+  unsigned fill = 0;
+  if(producer)
+    laneBackwardProducer<M, P>(model_in_constant_bank, ws, prm, sm, b, t, warp - CW, xs, us, fill);
+  else
+  {
+    const M model = model_in_constant_bank;
+    laneBackwardConsumer<M, CONSTRAINED, XCH>(model, ws, prm, sm, b, t, lane, live, xs, iter, fill);
+  }
 }
 } // namespace ddp
 } // namespace nmpc_b200

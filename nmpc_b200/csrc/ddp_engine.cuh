@@ -25,6 +25,7 @@
 #include "ddp_backward_lanes.cuh"
 #include "ddp_forward_phased.cuh"
 #include "ddp_forward_split.cuh"
+#include "ddp_solve_tile.cuh"
 #include "ddp_mpc.cuh"
 #include "registry.h"
 
@@ -433,6 +434,29 @@ public:
     ms[5] = fwd;
     ms[2] = el(2, end_opt); // opt (includes any active-count polls)
     ms[0] = el(0, end_opt); // solve
+    if(persistent_last_ && persistent_timed_)
+    {
+      // one kernel: the stage durations come from its own %globaltimer stamps (maximum over the tiles, per iteration)
+      std::vector<unsigned long long> ns(4 * (size_t)(cfg_.max_iter + 1));
+      NMPC_CUDA_CHECK(cudaMemcpy(ns.data(), stage_ns_.ptr, sizeof(unsigned long long) * ns.size(), cudaMemcpyDeviceToHost));
+      const double k0 = 1e-6 * double(ns[1]);
+      double b = 0, f = 0;
+      const int tiles = (B_ + kTile - 1) / kTile;
+      const bool dump = std::getenv("NMPC_B200_TILE_DUMP") != nullptr;
+      for(int it = 1; it <= cfg_.max_iter; it++)
+      {
+        b += 1e-6 * double(ns[4 * (size_t)it]);
+        f += 1e-6 * double(ns[4 * (size_t)it + 1]);
+        if(dump)
+          std::fprintf(stderr, "iter %d: bwd max %.1f mean %.1f us, fwd max %.1f mean %.1f us\n", it, 1e-3 * double(ns[4 * (size_t)it]),
+                       1e-3 * double(ns[4 * (size_t)it + 2]) / tiles, 1e-3 * double(ns[4 * (size_t)it + 1]),
+                       1e-3 * double(ns[4 * (size_t)it + 3]) / tiles);
+      }
+      ms[1] += k0;
+      ms[2] = std::max(0.0, ms[2] - k0);
+      ms[4] = b;
+      ms[5] = f;
+    }
     // copy_out: every get() since the last solve() recorded a pair after end_opt
     double out = 0;
     for(int e = end_opt + 1; e + 1 < n_events_used_; e += 2) out += el(e, e + 1);
@@ -497,6 +521,15 @@ protected:
     const int N = cfg_.horizon_steps;
     prm_.t0 = S(current_t);
     launches_[0] = launches_[1] = launches_[2] = launches_[3] = 0;
+    persistent_last_ = false;
+    if constexpr(kLanesOk)
+    {
+      if(usePersistent(B))
+      {
+        launchSolveTile(B, st);
+        return;
+      }
+    }
     const int tpb = threadsPerBlock(B);
     const int grid = (B + tpb - 1) / tpb;
     launchPdl(rollout_init_kernel<M>, dim3(grid), dim3(tpb), 0, st, model_, ws_, prm_);
@@ -537,6 +570,51 @@ protected:
   {
     const char * env = std::getenv(name);
     return env != nullptr ? std::atoi(env) : dflt;
+  }
+
+  /** One persistent CTA per 32-instance tile for the whole solve (ddp_solve_tile.cuh): while every tile has an SM of
+      its own.  Beyond that the tiles would queue up behind whole solves and the stage kernels take over. */
+  bool usePersistent(int B) const
+  {
+    return kLanesOk && use_fused_ && tile_variant_ != 0 && B <= tile_max_batch_;
+  }
+
+  void launchSolveTile(int B, cudaStream_t st)
+  {
+    if constexpr(kLanesOk)
+    {
+      using XS = XchSmem<S, LaneLayout<M>::G>;
+      ensureFanout();
+      const size_t smem = TileSmem<M>::bytes();
+      const int tiles = (B + kTile - 1) / kTile;
+      unsigned long long * stage_ns = nullptr;
+      if(timing_)
+      {
+        stage_ns_.reserve(4 * (size_t)(cfg_.max_iter + 1));
+        NMPC_CUDA_CHECK(cudaMemsetAsync(stage_ns_.ptr, 0, sizeof(unsigned long long) * 4 * (size_t)(cfg_.max_iter + 1), st));
+        stage_ns = stage_ns_.ptr;
+      }
+      record(st); // 2: (the initial rollout is inside the kernel)
+      iter_event_base_ = n_events_used_;
+      iters_launched_ = 0;
+      auto launch = [&](auto kernel, bool & attr_set) {
+        if(!attr_set)
+        {
+          NMPC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr_set = true;
+        }
+        launchPdl(kernel, dim3(tiles), dim3(kTileWarps * 32), smem, st, model_, ws_, prm_, fan_, stage_ns);
+      };
+      if(cfg_.with_input_constraint)
+        launch(ddp_solve_tile_kernel<M, true, XS>, tile_attr_set_[1]);
+      else
+        launch(ddp_solve_tile_kernel<M, false, XS>, tile_attr_set_[0]);
+      launches_[0] = 1;
+      persistent_last_ = true;
+      persistent_timed_ = timing_;
+      record(st); // end of optimisation loop
+      NMPC_CUDA_CHECK(cudaGetLastError());
+    }
   }
 
   static constexpr int kMaxThreadsPerBlock = 128;
@@ -819,7 +897,11 @@ protected:
   {
     using O = FwdOperands<NX, NU>;
     ensureFanout();
-    if(fwd_split_ != 0)
+    // the split rings (two steps per stage) must fit an SM's shared memory: not for many inputs (centroidal motion 9 x 16)
+    constexpr size_t kSplitFirstBytes = sizeof(S) * (SplitLayout<M>::inElems(kTile) + SplitLayout<M>::outElems(kTile)) + 256;
+    constexpr bool kSplitFits = kSplitFirstBytes <= 200 * 1024 && FanSmem<M>::bytes() <= 200 * 1024;
+    const bool split = kSplitFits && fwd_split_ != 0 && B <= fwd_split_max_batch_;
+    if(split)
     {
       // one 32-instance tile per CTA: rollout warp + cost warp + loader warp (ddp_forward_split.cuh)
       using SL = SplitLayout<M>;
@@ -845,12 +927,10 @@ protected:
       }
       launchPdl(forward_first_kernel<M>, dim3((B + kTile - 1) / kTile), dim3(64), smem, st, model_, ws_, prm_, fan_, iter);
     }
-    if(fwd_split_ != 0)
+    if(split)
     {
-      using SL = SplitLayout<M>;
-      constexpr int ipc = kFanWarps * (32 / kFanLanes); // listed instances per CTA
-      const size_t smem = sizeof(S) * ((size_t)kSplitIn * kSPS * ipc * O::SIZE + (size_t)kFanWarps * SL::outElems(kTile))
-                          + sizeof(unsigned long long) * (2 * kSplitIn + 2 * kSplitOut * kFanWarps) + 16;
+      constexpr int ipc = FanSmem<M>::IPC; // listed instances per CTA
+      const size_t smem = FanSmem<M>::bytes();
       bool & attr_set = lanes_attr_set_[11];
       if(!attr_set)
       {
@@ -1072,8 +1152,15 @@ protected:
   bool lanes_attr_set_[12] = {};
   int lanes_variant_ = envInt("NMPC_B200_BWD_LANES", 1); //!< 0: thread per instance, 1: G lanes, smem exchange, 2: shuffles
   int lanes_tiles_per_cta_ = envInt("NMPC_B200_BWD_LANES_TPC", 1); //!< 32-instance tiles per CTA
-  int fwd_split_ = envInt("NMPC_B200_FWD_SPLIT", 1); //!< phase 1 of the line search with rollout / cost / loader warps
-  int lanes_max_batch_ = envInt("NMPC_B200_BWD_LANES_MAXB", 16384);
+  int tile_variant_ = envInt("NMPC_B200_TILE", 0); //!< 1: persistent CTA per tile while B <= tile_max_batch_ (measured slower)
+  int tile_max_batch_ = envInt("NMPC_B200_TILE_MAXB", 148 * kTile);
+  bool tile_attr_set_[2] = {false, false};
+  bool persistent_last_ = false; //!< the last solve ran in the persistent kernel
+  bool persistent_timed_ = false;
+  DeviceBuffer<unsigned long long> stage_ns_;
+  int fwd_split_ = envInt("NMPC_B200_FWD_SPLIT", 1); //!< line search with rollout / cost / loader warps
+  int fwd_split_max_batch_ = envInt("NMPC_B200_FWD_SPLIT_MAXB", 12288); //!< measured: 0.94 vs 1.03 ms at 8192, 1.63 vs 1.58 at 16384
+  int lanes_max_batch_ = envInt("NMPC_B200_BWD_LANES_MAXB", 148 * kTile); //!< one tile per SM; beyond, the thread-per-instance sweep wins
   bool limits_vary_ = false; //!< the limits differ between horizon steps
   bool timing_ = false;
   std::vector<cudaEvent_t> events_;

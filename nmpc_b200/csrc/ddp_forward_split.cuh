@@ -48,7 +48,7 @@ struct SplitLayout
 /** Rollout role.  Operand e of step slot q of in-stage st is in_ring[(st * kSPS + q) * IN_STAGE + in_off + e * IN_ES];
     this lane's out column is out_col (element r of slot q of out-stage so at out_col[((so * kSPS + q) * OUT + r) * 32]).
     Every lane of the warp runs the loop. */
-template<class M, int IN_STAGE, int IN_ES>
+template<class M, int IN_STAGE, int IN_ES, bool INIT = false>
 __device__ __forceinline__ void splitRollout(const M & model,
                                              typename M::Scalar t0,
                                              int N,
@@ -60,7 +60,9 @@ __device__ __forceinline__ void splitRollout(const M & model,
                                              unsigned long long * in_empty,
                                              typename M::Scalar * out_col,
                                              unsigned long long * out_full,
-                                             unsigned long long * out_empty)
+                                             unsigned long long * out_empty,
+                                             unsigned in_base = 0,
+                                             unsigned out_base = 0)
 {
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
@@ -79,13 +81,30 @@ __device__ __forceinline__ void splitRollout(const M & model,
 #pragma unroll
     for(int d = 0; d < NU * NX; d++) Kr[d] = op[(size_t)(O::KFB + d) * IN_ES];
     Matrix<S, NU, 1> u;
-#pragma unroll
-    for(int c = 0; c < NU; c++)
+    if constexpr(INIT)
     {
-      S acc = S(0);
+      // solve()'s initial rollout (:83-96): the given inputs as they are; padding entries of a time-varying input
+      // dimension are forced to zero (and stored so by the cost role)
 #pragma unroll
-      for(int j = 0; j < NX; j++) acc += Kr[c + j * NU] * (x[j] - xr[j]);
-      u[c] = (ur[c] + alpha * kr[c]) + acc; // u' = u + alpha k + K (x' - x)   (:545-546)
+      for(int c = 0; c < NU; c++) u[c] = ur[c];
+      if constexpr(HasInputDim<M>::value)
+      {
+        const int nu_act = model.inputDim(t);
+#pragma unroll
+        for(int c = 0; c < NU; c++)
+          if(c >= nu_act) u[c] = S(0);
+      }
+    }
+    else
+    {
+#pragma unroll
+      for(int c = 0; c < NU; c++)
+      {
+        S acc = S(0);
+#pragma unroll
+        for(int j = 0; j < NX; j++) acc += Kr[c + j * NU] * (x[j] - xr[j]);
+        u[c] = (ur[c] + alpha * kr[c]) + acc; // u' = u + alpha k + K (x' - x)   (:545-546)
+      }
     }
 #pragma unroll
     for(int d = 0; d < NX; d++) oc[(size_t)d * kTile] = x[d];
@@ -99,9 +118,10 @@ __device__ __forceinline__ void splitRollout(const M & model,
   int g = 0;
   for(; g < n_pairs; g++, fi += S(kSPS))
   {
-    const int st = g % kSplitIn, so = g % kSplitOut;
-    mbarWait(&in_full[st], (unsigned)(g / kSplitIn) & 1u);
-    if(g >= kSplitOut) mbarWait(&out_empty[so], (unsigned)((g / kSplitOut) - 1) & 1u);
+    const unsigned gi = in_base + (unsigned)g, go = out_base + (unsigned)g;
+    const unsigned st = gi % kSplitIn, so = go % kSplitOut;
+    mbarWait(&in_full[st], (gi / kSplitIn) & 1u);
+    if(go >= (unsigned)kSplitOut) mbarWait(&out_empty[so], ((go / kSplitOut) - 1u) & 1u);
     const S * op = in_ring + (size_t)st * kSPS * IN_STAGE + in_off;
     S * oc = out_col + (size_t)so * kSPS * OUT * kTile;
 #pragma unroll
@@ -111,14 +131,15 @@ __device__ __forceinline__ void splitRollout(const M & model,
   }
   // tail: the odd last step (if any) and the terminal state share one out-stage; otherwise the terminal state alone
   {
-    const int so = g % kSplitOut;
-    if(g >= kSplitOut) mbarWait(&out_empty[so], (unsigned)((g / kSplitOut) - 1) & 1u);
+    const unsigned gi = in_base + (unsigned)g, go = out_base + (unsigned)g;
+    const unsigned so = go % kSplitOut;
+    if(go >= (unsigned)kSplitOut) mbarWait(&out_empty[so], ((go / kSplitOut) - 1u) & 1u);
     S * oc = out_col + (size_t)so * kSPS * OUT * kTile;
     int q = 0;
     if(N % kSPS != 0)
     {
-      const int st = g % kSplitIn;
-      mbarWait(&in_full[st], (unsigned)(g / kSplitIn) & 1u);
+      const unsigned st = gi % kSplitIn;
+      mbarWait(&in_full[st], (gi / kSplitIn) & 1u);
       step(in_ring + (size_t)st * kSPS * IN_STAGE + in_off, oc, t0 + fi * dt);
       mbarArrive(&in_empty[st]);
       q = 1;
@@ -127,6 +148,16 @@ __device__ __forceinline__ void splitRollout(const M & model,
     for(int d = 0; d < NX; d++) oc[((size_t)q * OUT + d) * kTile] = x[d];
     mbarArrive(&out_full[so]);
   }
+}
+
+/** Ring stages one rollout of N steps passes through. */
+__host__ __device__ constexpr unsigned splitInStages(int N)
+{
+  return (unsigned)((N + kSPS - 1) / kSPS);
+}
+__host__ __device__ constexpr unsigned splitOutStages(int N)
+{
+  return (unsigned)((N + 1 + kSPS - 1) / kSPS);
 }
 
 /** Cost role: running / terminal costs of the candidate published by the rollout role, their sum (in the order of
@@ -139,7 +170,8 @@ __device__ __forceinline__ typename M::Scalar splitCost(const M & model,
                                                         unsigned long long * out_full,
                                                         unsigned long long * out_empty,
                                                         bool store,
-                                                        const FwdDest<typename M::Scalar> & dst)
+                                                        const FwdDest<typename M::Scalar> & dst,
+                                                        unsigned out_base = 0)
 {
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
@@ -154,8 +186,9 @@ __device__ __forceinline__ typename M::Scalar splitCost(const M & model,
   const int n_stages = (N + 1 + kSPS - 1) / kSPS;
   for(int g = 0; g < n_stages; g++)
   {
-    const int so = g % kSplitOut;
-    mbarWait(&out_full[so], (unsigned)(g / kSplitOut) & 1u);
+    const unsigned go = out_base + (unsigned)g;
+    const unsigned so = go % kSplitOut;
+    mbarWait(&out_full[so], (go / kSplitOut) & 1u);
     const S * oc = out_col + (size_t)so * kSPS * OUT * kTile;
     S xv[kSPS][NX], uv[kSPS][NU];
 #pragma unroll
@@ -215,7 +248,8 @@ __device__ __forceinline__ void splitLoadTile(const Workspace<typename M::Scalar
                                               int sel,
                                               typename M::Scalar * in_ring,
                                               unsigned long long * in_full,
-                                              unsigned long long * in_empty)
+                                              unsigned long long * in_empty,
+                                              unsigned in_base = 0)
 {
   using S = typename M::Scalar;
   constexpr int NX = M::NX, NU = M::NU;
@@ -250,8 +284,9 @@ __device__ __forceinline__ void splitLoadTile(const Workspace<typename M::Scalar
   const int n_fills = (N + kSPS - 1) / kSPS;
   for(int f = 0; f < n_fills; f++)
   {
-    const int st = f % kSplitIn;
-    if(f >= kSplitIn) mbarWait(&in_empty[st], (unsigned)((f / kSplitIn) - 1) & 1u);
+    const unsigned fg = in_base + (unsigned)f;
+    const unsigned st = fg % kSplitIn;
+    if(fg >= (unsigned)kSplitIn) mbarWait(&in_empty[st], ((fg / kSplitIn) - 1u) & 1u);
     S * dstp = in_ring + (size_t)st * kSPS * O::SIZE * kTile + lane;
 #pragma unroll
     for(int q = 0; q < kSPS; q++)
@@ -353,41 +388,38 @@ __global__ void __launch_bounds__(96) forward_first_split_kernel(const __grid_co
   fan.list[slot] = b;
 }
 
-/** Phase 2 of the line search (see forward_fanout_kernel): candidates 1 .. n_alpha-1 of every listed instance at once,
-    16 lanes per listed instance, with the three roles above.  CTA = kFanWarps rollout warps + kFanWarps cost warps (warp
-    kFanWarps + w is the partner of warp w: same lane = same candidate) + one loader warp streaming the operands of the
-    CTA's eight instances (read as a broadcast by the lanes of a group). */
+/** Shared-memory carve-up of phase 2: one broadcast in-ring for the CTA's eight listed instances and one out-ring per
+    rollout / cost warp pair. */
 template<class M>
-__global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
-    forward_fanout_split_kernel(const __grid_constant__ M model_in_constant_bank,
-                                const __grid_constant__ Workspace<typename M::Scalar> ws,
-                                const __grid_constant__ SolverParams<typename M::Scalar> prm,
-                                const __grid_constant__ FwdFanout<typename M::Scalar> fan,
-                                int iter)
+struct FanSmem
 {
-  pdlPrologue();
   using S = typename M::Scalar;
-  constexpr int NX = M::NX, NU = M::NU;
   using SL = SplitLayout<M>;
-  using O = typename SL::O;
-  constexpr int GA = kFanLanes;
-  constexpr int IPW = 32 / GA; // listed instances per rollout warp
-  constexpr int IPC = kFanWarps * IPW; // ... per CTA
-  constexpr int ROWS = IPC * O::SIZE; // in-ring rows of one step: [instance of the CTA][operand]
-  constexpr unsigned kFull = 0xffffffffu;
-  constexpr unsigned kGroupMask = (1u << GA) - 1u;
-  const int count = *fan.count;
-  const int cta_slot0 = blockIdx.x * IPC;
-  if(cta_slot0 >= count) return; // CTA-uniform
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  S * in_ring = reinterpret_cast<S *>(smem_raw); // [kSplitIn][kSPS][ROWS]
-  S * out_ring = in_ring + (size_t)kSplitIn * kSPS * ROWS; // [kFanWarps][kSplitOut][kSPS][OUT][32]
-  unsigned long long * in_full = reinterpret_cast<unsigned long long *>(out_ring + (size_t)kFanWarps * SL::outElems(kTile));
-  unsigned long long * in_empty = in_full + kSplitIn;
-  unsigned long long * out_bars = in_empty + kSplitIn; // per pair: kSplitOut full, kSplitOut empty
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if(threadIdx.x == 0)
+  static constexpr int IPW = 32 / kFanLanes; //!< listed instances per rollout warp
+  static constexpr int IPC = kFanWarps * IPW; //!< ... per CTA and round
+  static constexpr int ROWS = IPC * SL::O::SIZE; //!< in-ring rows of one step: [instance][operand]
+  S * in_ring; //!< [kSplitIn][kSPS][ROWS]
+  S * out_ring; //!< [kFanWarps][kSplitOut][kSPS][OUT][32]
+  unsigned long long * in_full;
+  unsigned long long * in_empty;
+  unsigned long long * out_bars; //!< per pair: kSplitOut full, kSplitOut empty
+  static constexpr size_t bytes()
+  {
+    return ((sizeof(S) * ((size_t)kSplitIn * kSPS * ROWS + (size_t)kFanWarps * SL::outElems(kTile))
+             + sizeof(unsigned long long) * (2 * kSplitIn + 2 * kSplitOut * kFanWarps) + 127)
+            / 128)
+           * 128;
+  }
+  __device__ __forceinline__ explicit FanSmem(unsigned char * base)
+  {
+    in_ring = reinterpret_cast<S *>(base);
+    out_ring = in_ring + (size_t)kSplitIn * kSPS * ROWS;
+    in_full = reinterpret_cast<unsigned long long *>(out_ring + (size_t)kFanWarps * SL::outElems(kTile));
+    in_empty = in_full + kSplitIn;
+    out_bars = in_empty + kSplitIn;
+  }
+  /** One thread, before a CTA barrier. */
+  __device__ __forceinline__ void initBarriers() const
   {
     for(int st = 0; st < kSplitIn; st++)
     {
@@ -395,15 +427,57 @@ __global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
       mbarInit(&in_empty[st], kFanWarps * 32);
     }
     for(int st = 0; st < 2 * kSplitOut * kFanWarps; st++) mbarInit(&out_bars[st], 32);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  __syncthreads();
+  __device__ __forceinline__ S * outCol(int pair, int lane) const
+  {
+    return out_ring + (size_t)pair * SL::outElems(kTile) + lane;
+  }
+  __device__ __forceinline__ unsigned long long * outFull(int pair) const
+  {
+    return out_bars + (size_t)pair * 2 * kSplitOut;
+  }
+  __device__ __forceinline__ unsigned long long * outEmpty(int pair) const
+  {
+    return outFull(pair) + kSplitOut;
+  }
+};
+
+/** One round of phase 2 for the listed instances list[slot0 .. slot0 + IPC) (slots >= count are idle): candidates
+    1 .. n_alpha-1 of each at once, 16 lanes per instance.  Warps 0 .. kFanWarps-1 roll out, warp kFanWarps + w is
+    the cost partner of warp w (same lane = same candidate), warp 2 kFanWarps loads (the operands are read as a
+    broadcast by the lanes of a group).  Candidate trajectories go to the scratch columns (item_slot0 + instance of
+    the round) * 16 + candidate; the group then copies its winner into the instance's other buffer.  in_base /
+    out_base: ring stages already passed (the rings' mbarriers keep their phase across calls). */
+template<class M>
+__device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
+                                            const Workspace<typename M::Scalar> & ws,
+                                            const SolverParams<typename M::Scalar> & prm,
+                                            const FwdFanout<typename M::Scalar> & fan,
+                                            const FanSmem<M> & sm,
+                                            int iter,
+                                            const int * list,
+                                            int count,
+                                            int slot0,
+                                            size_t item_slot0,
+                                            int warp,
+                                            int lane,
+                                            unsigned in_base,
+                                            unsigned out_base)
+{
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX, NU = M::NU;
+  using O = typename SplitLayout<M>::O;
+  constexpr int GA = kFanLanes;
+  constexpr int IPW = FanSmem<M>::IPW;
+  constexpr int ROWS = FanSmem<M>::ROWS;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr unsigned kGroupMask = (1u << GA) - 1u;
   const size_t Bp = ws.Bp;
   const int N = prm.N;
 
   if(warp == 2 * kFanWarps)
   {
-    // loader: lane l streams in-ring rows l, l + 32, ... of every step; row = (instance of the CTA) * O::SIZE + operand
+    // loader: lane l streams in-ring rows l, l + 32, ... of every step; row = (instance of the round) * O::SIZE + operand
     constexpr int RPL = (ROWS + 31) / 32;
     const S * row_ptr[RPL];
     long long row_stride[RPL];
@@ -413,8 +487,8 @@ __global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
       const int row = q * 32 + lane;
       const int inst = (row < ROWS) ? row / O::SIZE : 0;
       const int e = (row < ROWS) ? row % O::SIZE : 0;
-      const int slot = cta_slot0 + inst;
-      const int b = fan.list[slot < count ? slot : cta_slot0]; // surplus slots repeat a valid instance
+      const int slot = slot0 + inst;
+      const int b = list[slot < count ? slot : slot0]; // surplus slots repeat a valid instance
       const int sel = ws.sel[b];
       if(e < O::U)
       {
@@ -437,11 +511,12 @@ __global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
         row_stride[q] = (long long)(NU * NX) * (long long)Bp;
       }
     }
-    const int n_fills = (N + kSPS - 1) / kSPS;
+    const int n_fills = (int)splitInStages(N);
     for(int f = 0; f < n_fills; f++)
     {
-      const int st = f % kSplitIn;
-      if(f >= kSplitIn) mbarWait(&in_empty[st], (unsigned)((f / kSplitIn) - 1) & 1u);
+      const unsigned fg = in_base + (unsigned)f;
+      const unsigned st = fg % kSplitIn;
+      if(fg >= (unsigned)kSplitIn) mbarWait(&sm.in_empty[st], ((fg / kSplitIn) - 1u) & 1u);
 #pragma unroll
       for(int sq = 0; sq < kSPS; sq++)
       {
@@ -453,48 +528,47 @@ __global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
           if(row < ROWS && in_range)
           {
             if constexpr(sizeof(S) == 8)
-              cpAsync8(in_ring + ((size_t)st * kSPS + sq) * ROWS + row, row_ptr[q]);
+              cpAsync8(sm.in_ring + ((size_t)st * kSPS + sq) * ROWS + row, row_ptr[q]);
             else
-              cpAsync4(in_ring + ((size_t)st * kSPS + sq) * ROWS + row, row_ptr[q]);
+              cpAsync4(sm.in_ring + ((size_t)st * kSPS + sq) * ROWS + row, row_ptr[q]);
           }
           row_ptr[q] += row_stride[q];
         }
       }
-      cpAsyncArriveOn(&in_full[st]);
+      cpAsyncArriveOn(&sm.in_full[st]);
     }
     return;
   }
+  if(warp > 2 * kFanWarps) return;
 
   const M model = model_in_constant_bank;
   const int pair = warp % kFanWarps;
   const int g = lane / GA;
   const int a = lane % GA;
-  const int inst = pair * IPW + g; // instance of the CTA
-  const int slot = cta_slot0 + inst;
+  const int inst = pair * IPW + g; // instance of the round
+  const int slot = slot0 + inst;
   const bool valid = slot < count;
-  const int b = fan.list[valid ? slot : cta_slot0];
+  const int b = list[valid ? slot : slot0];
   const int sel = ws.sel[b];
   const int rem = prm.n_alpha - 1;
   const bool work = valid && (a < rem);
   const S my_alpha = prm.alpha_list[work ? (1 + a) : 0];
-  S * out_col = out_ring + (size_t)pair * SL::outElems(kTile) + lane;
-  unsigned long long * out_full = out_bars + (size_t)pair * 2 * kSplitOut;
-  unsigned long long * out_empty = out_full + kSplitOut;
+  S * out_col = sm.outCol(pair, lane);
 
   if(warp < kFanWarps)
   {
     Matrix<S, NX, 1> x;
 #pragma unroll
     for(int d = 0; d < NX; d++) x[d] = ws.x[sel][(size_t)d * Bp + b];
-    splitRollout<M, ROWS, 1>(model, prm.t0, N, my_alpha, x, in_ring, inst * O::SIZE, in_full, in_empty, out_col, out_full,
-                             out_empty);
+    splitRollout<M, ROWS, 1>(model, prm.t0, N, my_alpha, x, sm.in_ring, inst * O::SIZE, sm.in_full, sm.in_empty, out_col,
+                             sm.outFull(pair), sm.outEmpty(pair), in_base, out_base);
     return;
   }
 
   // ------------------------------------------------------------------ cost warps
-  const size_t item = (size_t)slot * GA + a; // scratch column of this candidate
+  const size_t item = (item_slot0 + (size_t)inst) * GA + a; // scratch column of this candidate
   const FwdDest<S> dst{fan.sx, fan.su, fan.sc, fan.items, item};
-  const S my_cost = splitCost<M>(model, prm.t0, N, out_col, out_full, out_empty, work, dst);
+  const S my_cost = splitCost<M>(model, prm.t0, N, out_col, sm.outFull(pair), sm.outEmpty(pair), work, dst, out_base);
 
   const S cost_cur = ws.cost_sum[b];
   S my_actual = S(0), my_expected = S(0), my_ratio = S(0);
@@ -513,22 +587,19 @@ __global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
   const S r_alpha = __shfl_sync(kFull, my_alpha, src_lane);
   const bool success = valid && (gm != 0);
   if(valid && a == 0)
-  {
-    fan.commit_item[slot] = success ? (int)((size_t)slot * GA + pick) : -1;
     lineSearchFinish<S>(ws, prm, b, iter, sel, success, r_alpha, r_actual, r_expected, r_ratio, cost_cur, r_cost,
                         success ? (2 + pick) : prm.n_alpha);
-  }
   // Phase 3, fused: the group copies its winner's scratch trajectory into the instance's other buffer (which
   // lineSearchFinish has just made the current one).  The winner lane's global stores are ordered before the
   // group's loads by the warp barrier.
   __syncwarp();
   if(success)
   {
-    const size_t win = (size_t)slot * GA + pick;
+    const size_t win = (item_slot0 + (size_t)inst) * GA + pick;
     const int rows_x = (N + 1) * NX, rows_u = N * NU, rows_c = N + 1;
-    S * __restrict__ dx = ws.x[sel ^ 1];
-    S * __restrict__ du = ws.u[sel ^ 1];
-    S * __restrict__ dc = ws.cost[sel ^ 1];
+    S * dx = ws.x[sel ^ 1];
+    S * du = ws.u[sel ^ 1];
+    S * dc = ws.cost[sel ^ 1];
     const int rows = rows_x + rows_u + rows_c;
     auto src = [&](int r) -> const S * {
       return (r < rows_x) ? fan.sx + (size_t)r * fan.items + win
@@ -540,23 +611,49 @@ __global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
                           : (r < rows_x + rows_u) ? du + (size_t)(r - rows_x) * Bp + b
                                                   : dc + (size_t)(r - rows_x - rows_u) * Bp + b;
     };
-    for(int r0 = a; r0 < rows; r0 += GA * 8)
+    constexpr int kInFlight = 16;
+    for(int r0 = a; r0 < rows; r0 += GA * kInFlight)
     {
-      S v[8];
+      S v[kInFlight];
 #pragma unroll
-      for(int q = 0; q < 8; q++)
+      for(int q = 0; q < kInFlight; q++)
       {
         const int r = r0 + q * GA;
         if(r < rows) v[q] = *src(r);
       }
 #pragma unroll
-      for(int q = 0; q < 8; q++)
+      for(int q = 0; q < kInFlight; q++)
       {
         const int r = r0 + q * GA;
         if(r < rows) *dstp(r) = v[q];
       }
     }
   }
+}
+
+/** Phase 2 as a kernel of its own: CTA c serves the slots c * IPC .. of the global work list. */
+template<class M>
+__global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
+    forward_fanout_split_kernel(const __grid_constant__ M model_in_constant_bank,
+                                const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                const __grid_constant__ SolverParams<typename M::Scalar> prm,
+                                const __grid_constant__ FwdFanout<typename M::Scalar> fan,
+                                int iter)
+{
+  pdlPrologue();
+  const int count = *fan.count;
+  const int cta_slot0 = blockIdx.x * FanSmem<M>::IPC;
+  if(cta_slot0 >= count) return; // CTA-uniform
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const FanSmem<M> sm(smem_raw);
+  if(threadIdx.x == 0)
+  {
+    sm.initBarriers();
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  fanoutRound<M>(model_in_constant_bank, ws, prm, fan, sm, iter, fan.list, count, cta_slot0, (size_t)cta_slot0,
+                 threadIdx.x >> 5, threadIdx.x & 31, 0u, 0u);
 }
 } // namespace ddp
 } // namespace nmpc_b200

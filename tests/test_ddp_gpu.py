@@ -285,10 +285,20 @@ def test_full_size_batches_are_independent_of_the_kernel_variant(gpu, mode):
             setattr(big.config(), k, v)
         big.solve_batch(0.0, x0_all[:B], np.zeros((B, N, 1)))
         u = big.controlData().u_list
-        np.testing.assert_array_equal(u[:sub], want_u)
-        np.testing.assert_array_equal(big.cost()[:sub], want_cost)
-        np.testing.assert_array_equal(big.iterations()[:sub], want_it)
-        np.testing.assert_array_equal(big.n_forward()[:sub], want_fwd)
+        if B <= 4096:
+            # same kernel variants as the small batch (lanes K2, split K3): bit-identical
+            np.testing.assert_array_equal(u[:sub], want_u)
+            np.testing.assert_array_equal(big.cost()[:sub], want_cost)
+            np.testing.assert_array_equal(big.iterations()[:sub], want_it)
+            np.testing.assert_array_equal(big.n_forward()[:sub], want_fwd)
+        else:
+            # the large-batch variants (thread-per-instance K2: (Fx^T Vxx) Fx instead of Fx^T (Vxx Fx)) differ at
+            # rounding level
+            assert _rel_u(u[:sub], want_u).max() <= (U_TOL_REF if mode == "ref" else U_TOL_FIXED)
+            np.testing.assert_allclose(big.cost()[:sub], want_cost, rtol=COST_TOL_REF if mode == "ref" else COST_TOL_FIXED)
+            np.testing.assert_array_equal(big.iterations()[:sub], want_it)
+            if mode == "ref":
+                np.testing.assert_array_equal(big.n_forward()[:sub], want_fwd)
         assert _rel_u(u[:64], ref["u"]).max() <= (U_TOL_REF if mode == "ref" else U_TOL_FIXED)
         assert np.array_equal(big.iterations()[:64], ref["iters"])
         it = big.iterations()
@@ -302,13 +312,17 @@ def test_full_size_batches_are_independent_of_the_kernel_variant(gpu, mode):
         big.close()
 
 
-@pytest.mark.parametrize("env", [{"NMPC_B200_BWD_FUSED": "0"}, {"NMPC_B200_BWD_QUAD": "1"}, {"NMPC_B200_BWD_GS": "4"},
-                                 {"NMPC_B200_FWD_GA": "1"}, {"NMPC_B200_FWD_GA": "16"}])
+@pytest.mark.parametrize("env", [{"NMPC_B200_BWD_LANES": "0"}, {"NMPC_B200_BWD_LANES": "2"}, {"NMPC_B200_BWD_LANES_TPC": "2"},
+                                 {"NMPC_B200_BWD_FUSED": "0"}, {"NMPC_B200_BWD_QUAD": "1"}, {"NMPC_B200_BWD_GS": "4"},
+                                 {"NMPC_B200_FWD_SPLIT": "0"}, {"NMPC_B200_FWD_SPLIT": "0", "NMPC_B200_FWD_GA": "1"},
+                                 {"NMPC_B200_FWD_SPLIT": "0", "NMPC_B200_FWD_GA": "16"}, {"NMPC_B200_TILE": "1"}])
 def test_every_kernel_variant_agrees_with_the_default(gpu, env, monkeypatch):
-    """The K2 variants (three-kernel pipeline with the TMA tile ring, column-split over 4 warps, in-warp cooperative)
-    and the K3 variants (in-warp fan-out, 16-lane speculation) behind their environment switches against the default
-    (fused K1+K2, phased K3), with and without input limits: bit-identical controls, costs and counters, except the
-    in-warp cooperative K2, whose different product association is held to the M-ref tolerances."""
+    """The engine's other kernel variants behind their environment switches against the default (K1+K2 with four lanes
+    per instance, K3 split over rollout / cost / loader warps), with and without input limits.  Same arithmetic =>
+    bit-identical controls, costs and counters: the shuffle exchange and two tiles per CTA of the lanes K2, every K3
+    variant, the persistent tile kernel.  The thread-per-instance K2 family (fused, three-kernel pipeline, column
+    split over 4 warps, in-warp cooperative) associates (Fx^T Vxx) Fx instead of Fx^T (Vxx Fx) and is held to the M-ref
+    tolerances."""
     p = O.default_params("cartpole")
     B, Nh = 200, 100
     x0, u0 = O.cartpole_x0(B, 21), np.zeros((B, Nh, 1))
@@ -326,7 +340,8 @@ def test_every_kernel_variant_agrees_with_the_default(gpu, env, monkeypatch):
     base = [run(False), run(True)]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    exact = "NMPC_B200_BWD_GS" not in env  # the in-warp cooperative K2 associates Fx^T (Vxx Fx): rounding-level differences
+    exact = not any(k in env for k in ("NMPC_B200_BWD_GS", "NMPC_B200_BWD_FUSED", "NMPC_B200_BWD_QUAD")) and env.get(
+        "NMPC_B200_BWD_LANES") != "0"
     for want, box in zip(base, (False, True)):
         got = run(box)
         if exact:

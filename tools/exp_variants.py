@@ -49,7 +49,7 @@ def parity(mode, ref_cache):
     return out
 
 
-def timing(B, N=100):
+def timing(B, N=100, mode="fixed"):
     import torch
 
     p = O.default_params("cartpole")
@@ -57,7 +57,9 @@ def timing(B, N=100):
     u0 = torch.zeros((B, N, 1), dtype=torch.float64, device="cuda")
     s = nmpc_b200.DDPSolver("cartpole", params=p, batch_capacity=B)
     c = s.config()
-    c.horizon_steps, c.max_iter, c.k_rel_norm_thre, c.cost_update_thre = N, 10, 0.0, 0.0
+    c.horizon_steps, c.max_iter = N, 10
+    if mode == "fixed":
+        c.k_rel_norm_thre, c.cost_update_thre = 0.0, 0.0
     st = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     s.enable_timing(True)
@@ -70,7 +72,7 @@ def timing(B, N=100):
             if r >= 3:
                 rows.append([d[k] for k in ("solve", "setup", "backward", "forward")])
     med = np.median(np.array(rows), axis=0)
-    out = {"batch": B, "horizon": N, "solve_ms": float(med[0]), "setup_ms": float(med[1]), "backward_ms": float(med[2]),
+    out = {"batch": B, "horizon": N, "mode": mode, "iters_mean": float(s.iterations().mean()), "solve_ms": float(med[0]), "setup_ms": float(med[1]), "backward_ms": float(med[2]),
            "forward_ms": float(med[3]), "traj_per_s": B / (med[0] * 1e-3),
            "n_fwd_mean": float(s.n_forward().mean()), "n_bwd_mean": float(s.n_backward().mean())}
     s.close()
@@ -83,6 +85,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "exp_variants.json"))
     ap.add_argument("--horizon", type=int, nargs="+", default=[100])
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--mode", default="fixed", choices=["fixed", "ref"])
     ap.add_argument("variants", nargs="*")
     args = ap.parse_args()
     variants = args.variants or ["default="]
@@ -100,7 +103,7 @@ def main():
             if not args.no_parity:
                 res["parity_ref"] = parity("ref", ref_cache)
                 res["parity_fixed"] = parity("fixed", ref_cache)
-            res["timing"] = [timing(B, N) for B in args.batch for N in args.horizon]
+            res["timing"] = [timing(B, N, args.mode) for B in args.batch for N in args.horizon]
         except Exception as e:  # keep going: one broken variant must not hide the others
             res["error"] = repr(e)[:300]
         results[name] = res
