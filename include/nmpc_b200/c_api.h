@@ -186,6 +186,12 @@ extern "C"
       of launches of {rollout, derivative, backward, forward} kernels in the last solve. */
   int nmpc_b200_ddp_enable_timing(nmpc_b200_ddp * h, int enable);
   int nmpc_b200_ddp_get_durations(nmpc_b200_ddp * h, double * ms, int * launches);
+  /** TraceData::duration_derivative / duration_backward / duration_forward of every trace entry of the last solve
+      (DDPSolver.h:208-215; the last three columns of dumpTraceDataList(), DDPSolver.hpp:567-596), from the same stage
+      events: ms[rows][4] = {derivative, backward, first line-search candidate, other candidates} in ms; row 0 is the
+      iter-0 entry (initial rollout in column 2), duration_forward = columns 2 + 3.  The batch runs every stage as one
+      launch, so the durations of an iteration are those of the whole batch.  *rows_filled = entries available. */
+  int nmpc_b200_ddp_get_iteration_durations(nmpc_b200_ddp * h, double * ms, int rows, int * rows_filled);
 
   /* ------------------------------------------------------- receding-horizon (MPC) loop ---- */
 

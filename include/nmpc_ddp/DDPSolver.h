@@ -343,11 +343,21 @@ protected:
     }
     for(int i = 0; i < N; i++)
       for(int d = 0; d < InputDim; d++) control_data_.u_list[i][d] = u[(size_t)i * InputDim + d];
+    // duration_derivative / _backward / _forward per trace entry (DDPSolver.h:208-215): the stage events of the batch
+    std::vector<double> dur((size_t)(config_.max_iter + 1) * 4, 0.0);
+    int n_dur = 0;
+    nmpc_b200::throwOnError(nmpc_b200_ddp_get_iteration_durations(handle_, dur.data(), config_.max_iter + 1, &n_dur));
     trace_data_list_.clear();
     for(int r = 0; r < n_trace[0]; r++)
     {
       const double * row = &tr[(size_t)r * 9];
       TraceData t;
+      if(r < n_dur)
+      {
+        t.duration_derivative = dur[(size_t)r * 4 + 0];
+        t.duration_backward = dur[(size_t)r * 4 + 1];
+        t.duration_forward = dur[(size_t)r * 4 + 2] + dur[(size_t)r * 4 + 3];
+      }
       t.iter = static_cast<int>(row[0]);
       t.cost = row[1];
       t.lambda = row[2];

@@ -363,6 +363,16 @@ int nmpc_b200_ddp_get_durations(nmpc_b200_ddp * h, double * ms, int * launches)
   });
 }
 
+int nmpc_b200_ddp_get_iteration_durations(nmpc_b200_ddp * h, double * ms, int rows, int * rows_filled)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_HANDLE(h);
+    if(ms == nullptr || rows <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null or empty output");
+    const int n = h->engine->getIterationDurations(ms, rows);
+    if(rows_filled != nullptr) *rows_filled = n;
+  });
+}
+
 /* ------------------------------------------------------------------------------ FMPC ---- */
 
 void nmpc_b200_fmpc_config_default(nmpc_b200_fmpc_config * cfg)

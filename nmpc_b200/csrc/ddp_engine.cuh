@@ -405,6 +405,47 @@ public:
     timing_ = enable;
   }
 
+  /** TraceData::duration_derivative / _backward / _forward of every iteration (DDPSolver.h:208-215) from the stage
+      events of the last solve: ms[rows][4] = {derivative, backward, first line-search candidate, other candidates};
+      row 0 is the initial rollout (column 2).  Returns the number of rows filled. */
+  int getIterationDurations(double * ms, int rows) override
+  {
+    DeviceGuard guard(device_);
+    if(!timing_ || n_events_used_ < 4 || rows <= 0) return 0;
+    NMPC_CUDA_CHECK(cudaStreamSynchronize(last_stream_));
+    auto el = [&](int a, int b) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, events_[a], events_[b]);
+      return double(t);
+    };
+    for(int i = 0; i < 4 * rows; i++) ms[i] = 0.0;
+    if(persistent_last_)
+    {
+      if(!persistent_timed_) return 0;
+      const int n = std::min(rows, cfg_.max_iter + 1);
+      std::vector<unsigned long long> ns(4 * (size_t)(cfg_.max_iter + 1));
+      NMPC_CUDA_CHECK(cudaMemcpy(ns.data(), stage_ns_.ptr, sizeof(unsigned long long) * ns.size(), cudaMemcpyDeviceToHost));
+      ms[2] = 1e-6 * double(ns[1]);
+      for(int it = 1; it < n; it++)
+      {
+        ms[4 * it + 1] = 1e-6 * double(ns[4 * (size_t)it]);
+        ms[4 * it + 2] = 1e-6 * double(ns[4 * (size_t)it + 1]);
+      }
+      return n;
+    }
+    ms[2] = el(1, 2);
+    const int n = std::min(rows, iters_launched_ + 1);
+    for(int it = 1; it < n; it++)
+    {
+      const int e = iter_event_base_ + kEventsPerIter * (it - 1);
+      ms[4 * it + 0] = el(e - 1, e);
+      ms[4 * it + 1] = el(e, e + 1);
+      ms[4 * it + 2] = el(e + 1, e + 2);
+      ms[4 * it + 3] = el(e + 2, e + 3);
+    }
+    return n;
+  }
+
   void getDurations(double * ms, int * launches) override
   {
     DeviceGuard guard(device_);
@@ -418,16 +459,16 @@ public:
       cudaEventElapsedTime(&t, events_[a], events_[b]);
       return double(t);
     };
-    const int end_opt = iter_event_base_ + 3 * iters_launched_;
+    const int end_opt = iter_event_base_ + kEventsPerIter * iters_launched_;
     ms[6] = el(0, 1); // copy_in
     ms[1] = el(1, 2); // setup: layout + initial rollout
     double der = 0, bwd = 0, fwd = 0;
     for(int it = 0; it < iters_launched_; it++)
     {
-      const int e = iter_event_base_ + 3 * it;
+      const int e = iter_event_base_ + kEventsPerIter * it;
       der += el(e - 1, e);
       bwd += el(e, e + 1);
-      fwd += el(e + 1, e + 2);
+      fwd += el(e + 1, e + 3);
     }
     ms[3] = der;
     ms[4] = bwd;
@@ -547,7 +588,7 @@ protected:
       record(st);
       launchBackward(B, tpb, grid, iter, st);
       record(st);
-      launchForward(B, tpb, grid, iter, st);
+      launchForward(B, tpb, grid, iter, st); // records the event between the two phases of the line search itself
       record(st);
       if(!fused) launches_[1]++;
       launches_[2]++;
@@ -617,6 +658,7 @@ protected:
     }
   }
 
+  static constexpr int kEventsPerIter = 4; //!< after Step 1, Step 2, the first line-search candidate, the other candidates
   static constexpr int kMaxThreadsPerBlock = 128;
   static constexpr bool kHasBoxQP = true;
   static constexpr size_t kQuadSmemLimit = 200 * 1024; //!< shared memory the column-split K2 may use per CTA
@@ -927,6 +969,7 @@ protected:
       }
       launchPdl(forward_first_kernel<M>, dim3((B + kTile - 1) / kTile), dim3(64), smem, st, model_, ws_, prm_, fan_, iter);
     }
+    record(st); // first candidate done
     if(split)
     {
       constexpr int ipc = FanSmem<M>::IPC; // listed instances per CTA
@@ -977,10 +1020,11 @@ protected:
         break;
       case kPhased:
         launchForwardPhased(B, iter, st);
-        break;
+        return;
       default:
         launchPdl(forward_kernel<M>, dim3(grid), dim3(tpb), 0, st, model_, ws_, prm_, iter);
     }
+    record(st); // single-kernel line search: the whole of it counts as "first candidate"
   }
 
   /** Largest CTA whose two-stage block ring fits the 227 KB of shared memory an SM offers. */

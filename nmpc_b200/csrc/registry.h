@@ -50,6 +50,7 @@ public:
   virtual void sync() = 0;
   virtual void enableTiming(bool enable) = 0;
   virtual void getDurations(double * ms, int * launches) = 0;
+  virtual int getIterationDurations(double * ms, int rows) = 0;
 };
 
 /** Batched FMPC solver bound to one functor type. */

@@ -224,13 +224,25 @@ class DDPSolver:
         """traceDataList() of one instance (DDPSolver.h:294-297)."""
         tr = self.trace()[instance]
         n = int(self.n_trace()[instance])
+        dur = self.iterationDurations()
         out = []
         for r in range(n):
             row = tr[r]
+            d = dur[r] if r < len(dur) else (0.0, 0.0, 0.0, 0.0)
             out.append(TraceData(iter=int(row[0]), cost=row[1], lambda_=row[2], dlambda=row[3], alpha=row[4],
                                  k_rel_norm=row[5], cost_update_actual=row[6], cost_update_expected=row[7],
-                                 cost_update_ratio=row[8]))
+                                 cost_update_ratio=row[8], duration_derivative=float(d[0]),
+                                 duration_backward=float(d[1]), duration_forward=float(d[2] + d[3])))
         return out
+
+    def iterationDurations(self):
+        """[rows][4] ms per trace entry: derivative, backward, first line-search candidate, other candidates (the
+        stages of the whole batch; zeros unless enable_timing(True) was set before the solve)."""
+        rows = self._config.max_iter + 1
+        ms = np.zeros((rows, 4))
+        n = C.c_int(0)
+        check(lib().nmpc_b200_ddp_get_iteration_durations(self._h, ms.ctypes.data_as(C.c_void_p), rows, C.byref(n)))
+        return ms[:n.value]
 
     def dumpTraceDataList(self, file_path, instance=0):
         """Same 12-column, space-separated table as DDPSolver::dumpTraceDataList (DDPSolver.hpp:563-598)."""
