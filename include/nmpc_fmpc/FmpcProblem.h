@@ -3,7 +3,23 @@
  * include/nmpc_ddp/DDPProblem.h for how a problem is bound to its device functor. */
 #pragma once
 
+#include <type_traits>
+#include <utility>
+
 #include <nmpc_ddp/DDPProblem.h>
+
+namespace nmpc_b200
+{
+/** Does functor F declare a time-varying inequality dimension, `int ineqDim(t)`? */
+template<class F, class = void>
+struct HasIneqDimMethod : std::false_type
+{
+};
+template<class F>
+struct HasIneqDimMethod<F, std::void_t<decltype(std::declval<const F &>().ineqDim(0.0))>> : std::true_type
+{
+};
+} // namespace nmpc_b200
 
 namespace nmpc_fmpc
 {
@@ -24,13 +40,20 @@ public:
 public:
   FmpcProblem(double dt) : nmpc_ddp::DDPProblem<StateDim, InputDim>(dt)
   {
-    static_assert(IneqDim >= 0, "[FMPC] Template param IneqDim should be non-negative (dynamic size is not built yet).");
+    static_assert(IneqDim >= 0, "[FMPC] Template param IneqDim is the LARGEST inequality dimension of the problem.");
   }
 
+  /** The (largest) inequality dimension. */
   inline virtual int ineqDim() const
   {
     return IneqDim;
   }
+  /** The inequality dimension at time t (FmpcProblem.h:74-86).  The reference spells a time-varying dimension
+      FmpcProblem<S, I, Eigen::Dynamic> with this method overridden; a kernel needs compile-time sizes, so here IneqDim
+      is the largest dimension and the override returns how many LEADING rows of ineqConst / calcIneqConstDeriv are
+      constraints at t.  The solver keeps the other rows neutral (s = 1, nu = 0, C = D = 0): every active quantity
+      equals the reference's reduced-size result (tests/test_fmpc_extra.py, golden vectors of the reference's own
+      FmpcSolver<4, 1, Eigen::Dynamic>). */
   inline virtual int ineqDim(double // t
   ) const
   {
@@ -75,6 +98,13 @@ public:
   const F & functor() const
   {
     return functor_;
+  }
+  int ineqDim(double t) const override
+  {
+    if constexpr(nmpc_b200::HasIneqDimMethod<F>::value)
+      return functor_.ineqDim(t);
+    else
+      return F::NG;
   }
 
   StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const override

@@ -26,6 +26,7 @@
 #include <nmpc_b200/matrix.h>
 
 #include "ddp_kernels.cuh" // mbarrier / bulk-copy helpers, kTile
+#include "fmpc_linalg.cuh"
 
 namespace nmpc_b200
 {
@@ -168,6 +169,29 @@ __device__ __forceinline__ bool finite(S v)
   return !(isnan(v) || isinf(v));
 }
 
+/** Does the functor have a time-varying inequality dimension, `int ineqDim(t)` <= NG (FmpcProblem<.., Eigen::Dynamic>,
+    FmpcProblem.h:62-86)?  Rows j >= ineqDim(t_i) of step i are PADDING: F0 pins s = 1, nu = 0 there, F1 zeroes g + s, C
+    and D, F2 counts only real rows in the barrier average, F3 keeps delta s = delta nu = 0 and the merit function
+    ignores them.  Every active quantity then has the value the reference computes with vectors of size ineqDim(t)
+    (tests/golden/reference_fmpc_dynamic.npz: the reference's own FmpcSolver<4, 1, Eigen::Dynamic>). */
+template<class M, class = void>
+struct HasIneqDim : std::false_type
+{
+};
+template<class M>
+struct HasIneqDim<M, std::void_t<decltype(std::declval<const M &>().ineqDim(std::declval<typename M::Scalar>()))>>
+: std::true_type
+{
+};
+template<class M>
+__device__ __forceinline__ int ineqDimAt(const M & model, typename M::Scalar t)
+{
+  if constexpr(HasIneqDim<M>::value)
+    return model.ineqDim(t);
+  else
+    return M::NG;
+}
+
 /* ------------------------------------------------------------------------------------ F0 ---- */
 /** solve() prologue per (instance, step): optional init_complementary_variable (FmpcSolver.hpp:172-188)
     and the non-negativity part of checkVariable (:348-361); step 0 also resets the per-instance state. */
@@ -190,6 +214,7 @@ __global__ void fmpc_init_kernel(const __grid_constant__ M model,
     // value from the previous solve() -- the engine seeds it with initial_barrier_eps
     if(!prm.keep_barrier_eps) ws.barrier_eps[b] = prm.initial_barrier_eps;
   }
+  const int ng_act = ineqDimAt<M>(model, prm.t0 + i * model.dt());
   if(prm.init_complementary_variable)
   {
     const S margin_rate = S(1e-2);
@@ -208,8 +233,8 @@ __global__ void fmpc_init_kernel(const __grid_constant__ M model,
     {
       const S sj = (S(1) + margin_rate) * fmax(S(-1) * g[j], var_min);
       const S nj = (S(1) + margin_rate) * fmax(eps0 * (S(1) / sj), var_min);
-      ws.s[((size_t)i * NG + j) * Bp + b] = sj;
-      ws.nu[((size_t)i * NG + j) * Bp + b] = nj;
+      ws.s[((size_t)i * NG + j) * Bp + b] = (j < ng_act) ? sj : S(1);
+      ws.nu[((size_t)i * NG + j) * Bp + b] = (j < ng_act) ? nj : S(0);
     }
     if(i == 0) ws.barrier_eps[b] = eps0;
   }
@@ -219,7 +244,13 @@ __global__ void fmpc_init_kernel(const __grid_constant__ M model,
 #pragma unroll
     for(int j = 0; j < NG; j++)
     {
-      neg = neg || (ws.s[((size_t)i * NG + j) * Bp + b] < S(0)) || (ws.nu[((size_t)i * NG + j) * Bp + b] < S(0));
+      if(j < ng_act)
+        neg = neg || (ws.s[((size_t)i * NG + j) * Bp + b] < S(0)) || (ws.nu[((size_t)i * NG + j) * Bp + b] < S(0));
+      else
+      {
+        ws.s[((size_t)i * NG + j) * Bp + b] = S(1); // padding row of a time-varying inequality dimension
+        ws.nu[((size_t)i * NG + j) * Bp + b] = S(0);
+      }
     }
     if(neg) atomicExch(ws.bad_input, 1);
   }
@@ -303,7 +334,23 @@ __global__ void fmpc_coeff_kernel(const __grid_constant__ M model,
   model.calcRunningCostDeriv(t, x, u, Lx, Lu, Lxx, Luu, Lxu);
 
   const Matrix<S, NX, 1> x_bar = model.stateEq(t, x, u) - next_x; // (2.23c)
-  const Matrix<S, NG, 1> g_bar = model.ineqConst(t, x, u) + s; // (2.23d)
+  Matrix<S, NG, 1> g_bar = model.ineqConst(t, x, u) + s; // (2.23d)
+  if constexpr(HasIneqDim<M>::value)
+  {
+    const int ng_act = model.ineqDim(t);
+#pragma unroll
+    for(int j = 0; j < NG; j++)
+    {
+      if(j >= ng_act)
+      {
+        g_bar[j] = S(0);
+#pragma unroll
+        for(int c = 0; c < NX; c++) C(j, c) = S(0);
+#pragma unroll
+        for(int c = 0; c < NU; c++) D(j, c) = S(0);
+      }
+    }
+  }
   // (2.25b) Lx_bar = -lambda + dt Lx + A^T next_lambda + C^T nu
   Matrix<S, NX, 1> Lx_bar;
 #pragma unroll
@@ -433,6 +480,7 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
   if(prm.update_barrier_eps)
   {
     S s_nu_ave = S(0);
+    int total_ineq_dim = 0;
     for(int i = 0; i < N; i++)
     {
       S dotv = S(0);
@@ -440,8 +488,9 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
       for(int j = 0; j < NG; j++)
         dotv += ws.s[((size_t)i * NG + j) * Bp + b] * ws.nu[((size_t)i * NG + j) * Bp + b];
       s_nu_ave += dotv;
+      total_ineq_dim += ineqDimAt<M>(model, prm.t0 + i * dt); // s_list[i].size() (:388)
     }
-    s_nu_ave /= S(N * NG);
+    s_nu_ave /= S(total_ineq_dim);
     barrier_eps = fmin(fmax(S(0.5) * s_nu_ave, S(1e-8)), S(1e6));
     ws.barrier_eps[b] = barrier_eps;
   }
@@ -690,36 +739,8 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
     }
     else
     {
-      // general NU: unpivoted LDL^T (the reference's diagonal pivoting only reorders exact arithmetic)
-      S Lm[NU * NU], Dg[NU];
-#pragma unroll
-      for(int c = 0; c < NU; c++)
-      {
-        S dsum = G[c + c * NU];
-#pragma unroll
-        for(int q = 0; q < c; q++) dsum -= Lm[c + q * NU] * Lm[c + q * NU] * Dg[q];
-        Dg[c] = dsum;
-#pragma unroll
-        for(int r = c + 1; r < NU; r++)
-        {
-          S v = G[r + c * NU];
-#pragma unroll
-          for(int q = 0; q < c; q++) v -= Lm[r + q * NU] * Lm[c + q * NU] * Dg[q];
-          Lm[r + c * NU] = v / dsum;
-        }
-      }
-      auto solve = [&](S * rhs) {
-#pragma unroll
-        for(int r = 0; r < NU; r++)
-#pragma unroll
-          for(int q = 0; q < r; q++) rhs[r] -= Lm[r + q * NU] * rhs[q];
-#pragma unroll
-        for(int r = 0; r < NU; r++) rhs[r] /= Dg[r];
-#pragma unroll
-        for(int r = NU - 1; r >= 0; r--)
-#pragma unroll
-          for(int q = r + 1; q < NU; q++) rhs[r] -= Lm[q + r * NU] * rhs[q];
-      };
+      // general NU (:596-617): Eigen::LDLT with diagonal pivoting; if its info() is not Success either give up
+      // (break_if_llt_fails) or solve with Eigen::FullPivLU (fmpc_linalg.cuh)
 #pragma unroll
       for(int r = 0; r < NU; r++)
       {
@@ -728,19 +749,32 @@ __global__ void fmpc_backward_kernel(const __grid_constant__ M model,
         for(int q = 0; q < NX; q++) acc += Bm[q + r * NX] * Pxb_s[q];
         k[r] = acc + Lu_t[r];
       }
-      solve(k);
+#pragma unroll
+      for(int c = 0; c < NX; c++)
+#pragma unroll
+        for(int r = 0; r < NU; r++) K[r + c * NU] = H[c + r * NX]; // H^T
+      LdltFactor<S, NU> ldlt;
+      ldltCompute<S, NU>(G, ldlt);
+      if(ldlt.success)
+      {
+        ldltSolveInPlace<S, NU>(ldlt, k);
+        for(int c = 0; c < NX; c++) ldltSolveInPlace<S, NU>(ldlt, K + c * NU);
+      }
+      else if(prm.break_if_llt_fails)
+      {
+        llt_failed = true; // backwardPass() returns false (:608-611): ErrorInBackward
+      }
+      else
+      {
+        FullPivLuFactor<S, NU> lu;
+        fullPivLuCompute<S, NU>(G, lu);
+        fullPivLuSolveInPlace<S, NU>(lu, k);
+        for(int c = 0; c < NX; c++) fullPivLuSolveInPlace<S, NU>(lu, K + c * NU);
+      }
 #pragma unroll
       for(int r = 0; r < NU; r++) k[r] = S(-1) * k[r];
 #pragma unroll
-      for(int c = 0; c < NX; c++)
-      {
-        S col[NU];
-#pragma unroll
-        for(int r = 0; r < NU; r++) col[r] = H[c + r * NX];
-        solve(col);
-#pragma unroll
-        for(int r = 0; r < NU; r++) K[r + c * NU] = S(-1) * col[r];
-      }
+      for(int d = 0; d < NU * NX; d++) K[d] = S(-1) * K[d];
     }
 
     // post-process (:633-637): s = A^T (s - P x_bar) - Lx~ - H k ; P = F - K^T G K, symmetrised   (2.35a)
@@ -987,6 +1021,7 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
       nan_probe += du[r] * S(0);
     }
     // ds_i = -(C dx + D du + g_bar) ; dnu_i = -(nu (ds + s) - eps) / s               (2.27a-b)
+    const int ng_act = ineqDimAt<M>(model, prm.t0 + i * model.dt());
 #pragma unroll
     for(int j = 0; j < NG; j++)
     {
@@ -998,7 +1033,11 @@ __global__ void fmpc_forward_kernel(const __grid_constant__ M model,
       const S dsj = S(-1) * ((cdx + ddu) + op[(size_t)(R3::XG + NX + j) * kTile]);
       const S sj = op[(size_t)(R3::S_ + j) * kTile];
       const S nj = op[(size_t)(R3::NU_ + j) * kTile];
-      const S dnj = S(-1) * (nj * (dsj + sj) - barrier_eps) / sj;
+      S dnj = S(-1) * (nj * (dsj + sj) - barrier_eps) / sj;
+      if constexpr(HasIneqDim<M>::value)
+      {
+        if(j >= ng_act) dnj = S(0); // padding row: nu stays 0 (delta s is already -(0 + 0 + 0))
+      }
       ds_ptr[(size_t)j * Bp] = dsj;
       dnu_ptr[(size_t)j * Bp] = dnj;
       nan_probe += dsj * S(0) + dnj * S(0);
@@ -1120,9 +1159,10 @@ __device__ __forceinline__ typename M::Scalar fmpcMeritFunc(const M & model,
     }
     {
       const Matrix<S, NG, 1> g = model.ineqConst(t, x, u);
+      const int ng_act = ineqDimAt<M>(model, t);
       S l1 = S(0);
 #pragma unroll
-      for(int d = 0; d < NG; d++) l1 += fabs(g[d] + sv[d]);
+      for(int d = 0; d < NG; d++) l1 += (d < ng_act) ? fabs(g[d] + sv[d]) : S(0);
       con += l1;
     }
     x = xn;
@@ -1255,9 +1295,11 @@ __global__ void fmpc_linesearch_kernel(const __grid_constant__ M model,
       const Matrix<S, NG, 1> g = model.ineqConst(t, x, u);
       S l1 = S(0), dc = S(0), dd = S(0), dsl = S(0);
 #pragma unroll
+      const int ng_act = ineqDimAt<M>(model, t);
+#pragma unroll
       for(int r = 0; r < NG; r++)
       {
-        const S cf = g[r] + sv[r];
+        const S cf = (r < ng_act) ? g[r] + sv[r] : S(0); // padding rows: C = D = 0, delta s = 0
         l1 += fabs(cf);
         S jc = S(0), jd = S(0);
 #pragma unroll

@@ -336,6 +336,16 @@ int oracle_model_dims(const char * model, int * nx, int * nu, int * ng, int * np
     *nx = 2, *nu = 1, *ng = 3, *nparams = FmpcProblemOscillator::kNumParams;
     return 0;
   }
+  if(m == "fmpc_planar_quadrotor")
+  {
+    *nx = 6, *nu = 2, *ng = 4, *nparams = FmpcProblemPlanarQuadrotor::kNumParams;
+    return 0;
+  }
+  if(m == "fmpc_cartpole_windowed")
+  {
+    *nx = 4, *nu = 1, *ng = 4, *nparams = FmpcProblemCartPoleWindowed::kNumParams;
+    return 0;
+  }
   return -1;
 }
 
@@ -356,6 +366,10 @@ int oracle_model_default_params(const char * model, double * params)
     FmpcProblemCartPole::defaultParams(params);
   else if(m == "fmpc_oscillator")
     FmpcProblemOscillator::defaultParams(params);
+  else if(m == "fmpc_planar_quadrotor")
+    FmpcProblemPlanarQuadrotor::defaultParams(params);
+  else if(m == "fmpc_cartpole_windowed")
+    FmpcProblemCartPoleWindowed::defaultParams(params);
   else
     return -1;
   return 0;
@@ -465,6 +479,12 @@ int oracle_model_eval(const char * model,
   if(m == "fmpc_oscillator")
     return modelEval<FmpcProblemOscillator, 2, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx,
                                                   Vxx);
+  if(m == "fmpc_planar_quadrotor")
+    return modelEval<FmpcProblemPlanarQuadrotor, 6, 2>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx,
+                                                       Vxx);
+  if(m == "fmpc_cartpole_windowed")
+    return modelEval<FmpcProblemCartPoleWindowed, 4, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx,
+                                                        Vxx);
   return -2;
 }
 

@@ -42,6 +42,14 @@ public:
   {
     return NG;
   }
+  /** FmpcProblem<.., Eigen::Dynamic> (FmpcProblem.h:62-86): the inequality dimension at time t, at most NG.  Rows
+      j >= ineqDim(t) of a step are PADDING: the solver keeps s = 1, nu = 0 there and treats g + s, C, D as zero,
+      which leaves every active quantity at the value the reference computes with vectors of size ineqDim(t)
+      (pinned by tests/golden/reference_fmpc_dynamic.npz, produced by the reference's FmpcSolver<4, 1, Dynamic>). */
+  virtual int ineqDim(double) const
+  {
+    return NG;
+  }
   virtual IneqDimVector ineqConst(double t, const Vec<NX> & x, const Vec<NU> & u) const = 0; // FmpcProblem.h:94
   virtual void calcIneqConstDeriv(double t,
                                   const Vec<NX> & x,
@@ -139,6 +147,88 @@ struct LdltFactor
     for(int i = n - 1; i >= 0; i--)
       for(int j = i + 1; j < n; j++) y[i] -= a[j + i * n] * y[j];
     for(int i = 0; i < n; i++) b[perm[i]] = y[i];
+  }
+};
+
+/** Eigen::FullPivLU<Matrix<n,n>> (Eigen 3.4: complete pivoting, first maximum of |a| in column-major order of the
+    trailing block; solve() keeps the leading `rank` pivots, rank = #{|pivot| > epsilon * n * max|pivot|}, the other
+    solution components are zero).  The fallback of FmpcSolver.hpp:614-616. */
+struct FullPivLuFactor
+{
+  static constexpr int MAXN = 16;
+  double a[MAXN * MAXN];
+  int row_tr[MAXN];
+  int col_perm[MAXN];
+  int n = 0;
+  int rank = 0;
+
+  void compute(const double * a_in, int n_)
+  {
+    n = n_;
+    for(int j = 0; j < n; j++)
+      for(int i = 0; i < n; i++) a[i + j * n] = a_in[i + j * n];
+    for(int i = 0; i < n; i++)
+    {
+      row_tr[i] = i;
+      col_perm[i] = i;
+    }
+    double maxpivot = 0.0;
+    int nonzero = n;
+    for(int k = 0; k < n; k++)
+    {
+      int pr = k, pc = k;
+      double best = -1.0;
+      for(int j = k; j < n; j++)
+        for(int i = k; i < n; i++)
+        {
+          const double v = std::fabs(a[i + j * n]);
+          if(v > best)
+          {
+            best = v;
+            pr = i;
+            pc = j;
+          }
+        }
+      if(best == 0.0)
+      {
+        nonzero = k;
+        break;
+      }
+      if(best > maxpivot) maxpivot = best;
+      row_tr[k] = pr;
+      if(pr != k)
+        for(int j = 0; j < n; j++) std::swap(a[k + j * n], a[pr + j * n]);
+      if(pc != k)
+      {
+        for(int i = 0; i < n; i++) std::swap(a[i + k * n], a[i + pc * n]);
+        std::swap(col_perm[k], col_perm[pc]);
+      }
+      const double p = a[k + k * n];
+      for(int i = k + 1; i < n; i++) a[i + k * n] /= p;
+      for(int j = k + 1; j < n; j++)
+        for(int i = k + 1; i < n; i++) a[i + j * n] -= a[i + k * n] * a[k + j * n];
+    }
+    const double thr = std::numeric_limits<double>::epsilon() * n * maxpivot;
+    rank = 0;
+    for(int i = 0; i < nonzero; i++)
+      if(std::fabs(a[i + i * n]) > thr) rank++;
+  }
+
+  void solveInPlace(double * b) const
+  {
+    double c[MAXN];
+    for(int i = 0; i < n; i++) c[i] = b[i];
+    for(int k = 0; k < n; k++)
+      if(row_tr[k] != k) std::swap(c[k], c[row_tr[k]]);
+    for(int k = 0; k < n; k++)
+      for(int i = k + 1; i < n; i++) c[i] -= a[i + k * n] * c[k];
+    for(int i = rank - 1; i >= 0; i--)
+    {
+      double s = c[i];
+      for(int j = i + 1; j < rank; j++) s -= a[i + j * n] * c[j];
+      c[i] = s / a[i + i * n];
+    }
+    for(int i = 0; i < n; i++) b[col_perm[i]] = (i < rank) ? c[i] : 0.0;
   }
 };
 
@@ -339,6 +429,16 @@ public:
       }
     }
 
+    for(int i = 0; i < N; i++) // padding rows of a time-varying inequality dimension
+    {
+      const int ng_i = problem_->ineqDim(current_t_ + i * problem_->dt());
+      for(int j = ng_i; j < NG; j++)
+      {
+        variable_.s_list[i][j] = 1.0;
+        variable_.nu_list[i][j] = 0.0;
+      }
+    }
+
     checkVariable(); // .hpp:191
 
     if(delta_variable_.horizon_steps != N) // .hpp:194-198
@@ -424,7 +524,7 @@ protected:
       for(int i = 0; i < N; i++)
       {
         s_nu_ave += dot(variable_.s_list[i], variable_.nu_list[i]);
-        total_ineq_dim += NG;
+        total_ineq_dim += problem_->ineqDim(current_t_ + i * problem_->dt()); // s_list[i].size()
       }
       s_nu_ave /= total_ineq_dim;
 
@@ -456,6 +556,12 @@ protected:
 
         coeff.x_bar = sub(problem_->stateEq(t, x, u), next_x); // (2.23c)
         coeff.g_bar = add(problem_->ineqConst(t, x, u), s); // (2.23d)
+        for(int j = problem_->ineqDim(t); j < NG; j++) // padding rows: no constraint
+        {
+          coeff.g_bar[j] = 0.0;
+          for(int c = 0; c < NX; c++) coeff.C(j, c) = 0.0;
+          for(int c = 0; c < NU; c++) coeff.D(j, c) = 0.0;
+        }
         // (2.25b)  -1 * lambda + dt * Lx + A^T next_lambda + C^T nu
         coeff.Lx_bar = add(add(add(scale(-1, lambda), scale(dt, coeff.Lx)), mulT(coeff.A, next_lambda)),
                            mulT(coeff.C, nu));
@@ -596,10 +702,15 @@ protected:
           {
             return false;
           }
-          // The reference falls back to Eigen::FullPivLU (.hpp:614-616).  With diagonally pivoted
-          // LDLT this branch needs a zero pivot followed by a non-zero one; it is not reachable for
-          // NU == 1 and is not restated: fail loudly instead of guessing.
-          throw std::runtime_error("[oracle/FMPC] FullPivLU fallback reached; not restated.");
+          // Eigen::FullPivLU fallback (.hpp:614-616)
+          FullPivLuFactor lu;
+          lu.compute(G.d, NU);
+          InputDimVector rhs = add(mulT(B, sub(mul(P, x_bar), s)), Lu_tilde);
+          lu.solveInPlace(rhs.d);
+          k = scale(-1, rhs);
+          InputStateDimMatrix Ht = transpose(H);
+          for(int c = 0; c < NX; c++) lu.solveInPlace(&Ht.d[c * NU]);
+          K = scale(-1, Ht);
         }
       }
 
@@ -654,6 +765,11 @@ protected:
         delta_variable_.nu_list[i][j] =
             -1 * (variable_.nu_list[i][j] * (delta_variable_.s_list[i][j] + variable_.s_list[i][j]) - barrier_eps_)
             / variable_.s_list[i][j]; // (2.27b)
+      }
+      for(int j = problem_->ineqDim(current_t_ + i * problem_->dt()); j < NG; j++) // padding rows stay put
+      {
+        delta_variable_.s_list[i][j] = 0.0;
+        delta_variable_.nu_list[i][j] = 0.0;
       }
     }
 
@@ -818,6 +934,7 @@ protected:
       }
       {
         IneqDimVector const_func = add(problem_->ineqConst(t, x, u), s);
+        for(int d = problem_->ineqDim(t); d < NG; d++) const_func[d] = 0.0; // padding rows
         for(int d = 0; d < NG; d++) merit_func_const += std::fabs(const_func[d]);
         merit_deriv_const += l1NormDirectionalDeriv(const_func, coeff.C, delta_x);
         merit_deriv_const += l1NormDirectionalDeriv(const_func, coeff.D, delta_u);
@@ -883,6 +1000,7 @@ protected:
       }
       {
         IneqDimVector const_func = add(problem_->ineqConst(t, x, u), s);
+        for(int d = problem_->ineqDim(t); d < NG; d++) const_func[d] = 0.0; // padding rows
         for(int d = 0; d < NG; d++) merit_func_const += std::fabs(const_func[d]);
       }
     }

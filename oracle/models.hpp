@@ -635,6 +635,8 @@ protected:
 // what pins both is tests/golden/vertical_*: outputs of the reference's DDPSolver<2, Eigen::Dynamic> (oracle/ref).
 #include <nmpc_b200/models/centroidal_motion.h>
 #include <nmpc_b200/models/vertical_motion.h>
+#include <nmpc_b200/models/cartpole.h>
+#include <nmpc_b200/models/planar_quadrotor.h>
 
 namespace oracle
 {
@@ -740,4 +742,144 @@ using DDPProblemVerticalMotion = DDPProblemFromFunctor<nmpc_b200::models::Vertic
 // centroidal motion, n_x = 9, input dimension 16 or 0 (TestDDPCentroidalMotion.cpp:18-201); pinned by
 // tests/golden/reference_centroidal.npz (the reference's DDPSolver<9, Eigen::Dynamic>, oracle/ref/ref_centroidal.cpp)
 using DDPProblemCentroidalMotion = DDPProblemFromFunctor<nmpc_b200::models::CentroidalMotion<double>>;
+/** Any host+device FMPC functor F of include/nmpc_b200/models as an oracle problem (ineqDim(t) when F has it). */
+template<class F>
+class FmpcProblemFromFunctor : public FmpcProblem<F::NX, F::NU, F::NG>
+{
+public:
+  using Base = FmpcProblem<F::NX, F::NU, F::NG>;
+  using StateDimVector = Vec<F::NX>;
+  using InputDimVector = Vec<F::NU>;
+  using IneqDimVector = Vec<F::NG>;
+  using StateStateDimMatrix = Mat<F::NX, F::NX>;
+  using InputInputDimMatrix = Mat<F::NU, F::NU>;
+  using StateInputDimMatrix = Mat<F::NX, F::NU>;
+  using IneqStateDimMatrix = Mat<F::NG, F::NX>;
+  using IneqInputDimMatrix = Mat<F::NG, F::NU>;
+  static constexpr int kNumParams = F::NUM_PARAMS;
+  static constexpr int NX = F::NX, NU = F::NU, NG = F::NG;
+
+  explicit FmpcProblemFromFunctor(const double * p) : Base(p[0]), f_(F::fromParams(p)) {}
+  static void defaultParams(double * p)
+  {
+    F::defaultParams(p);
+  }
+  template<class A, class B>
+  static void copy(const A & a, B & b, int n)
+  {
+    for(int i = 0; i < n; i++) b.d[i] = a.d[i];
+  }
+  template<class G, class = void>
+  struct HasIneqDim : std::false_type
+  {
+  };
+  template<class G>
+  struct HasIneqDim<G, std::void_t<decltype(std::declval<const G &>().ineqDim(0.0))>> : std::true_type
+  {
+  };
+  int ineqDim(double t) const override
+  {
+    if constexpr(HasIneqDim<F>::value)
+      return f_.ineqDim(t);
+    else
+      return NG;
+  }
+  StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    typename F::StateDimVector fx, fn;
+    typename F::InputDimVector fu;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    fn = f_.stateEq(t, fx, fu);
+    StateDimVector out;
+    copy(fn, out, NX);
+    return out;
+  }
+  double runningCost(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    typename F::StateDimVector fx;
+    typename F::InputDimVector fu;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    return f_.runningCost(t, fx, fu);
+  }
+  double terminalCost(double t, const StateDimVector & x) const override
+  {
+    typename F::StateDimVector fx;
+    copy(x, fx, NX);
+    return f_.terminalCost(t, fx);
+  }
+  IneqDimVector ineqConst(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    typename F::StateDimVector fx;
+    typename F::InputDimVector fu;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    const typename F::IneqDimVector g = f_.ineqConst(t, fx, fu);
+    IneqDimVector out;
+    copy(g, out, NG);
+    return out;
+  }
+  void calcStateEqDeriv(double t, const StateDimVector & x, const InputDimVector & u, StateStateDimMatrix & Fx,
+                        StateInputDimMatrix & Fu) const override
+  {
+    typename F::StateDimVector fx;
+    typename F::InputDimVector fu;
+    typename F::StateStateDimMatrix a;
+    typename F::StateInputDimMatrix b;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    f_.calcStateEqDeriv(t, fx, fu, a, b);
+    copy(a, Fx, NX * NX);
+    copy(b, Fu, NX * NU);
+  }
+  void calcRunningCostDeriv(double t, const StateDimVector & x, const InputDimVector & u, StateDimVector & Lx,
+                            InputDimVector & Lu, StateStateDimMatrix & Lxx, InputInputDimMatrix & Luu,
+                            StateInputDimMatrix & Lxu) const override
+  {
+    typename F::StateDimVector fx, lx;
+    typename F::InputDimVector fu, lu;
+    typename F::StateStateDimMatrix lxx;
+    typename F::InputInputDimMatrix luu;
+    typename F::StateInputDimMatrix lxu;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    f_.calcRunningCostDeriv(t, fx, fu, lx, lu, lxx, luu, lxu);
+    copy(lx, Lx, NX);
+    copy(lu, Lu, NU);
+    copy(lxx, Lxx, NX * NX);
+    copy(luu, Luu, NU * NU);
+    copy(lxu, Lxu, NX * NU);
+  }
+  void calcTerminalCostDeriv(double t, const StateDimVector & x, StateDimVector & Vx, StateStateDimMatrix & Vxx)
+      const override
+  {
+    typename F::StateDimVector fx, vx;
+    typename F::StateStateDimMatrix vxx;
+    copy(x, fx, NX);
+    f_.calcTerminalCostDeriv(t, fx, vx, vxx);
+    copy(vx, Vx, NX);
+    copy(vxx, Vxx, NX * NX);
+  }
+  void calcIneqConstDeriv(double t, const StateDimVector & x, const InputDimVector & u, IneqStateDimMatrix & C,
+                          IneqInputDimMatrix & D) const override
+  {
+    typename F::StateDimVector fx;
+    typename F::InputDimVector fu;
+    typename F::IneqStateDimMatrix c;
+    typename F::IneqInputDimMatrix d;
+    copy(x, fx, NX);
+    copy(u, fu, NU);
+    f_.calcIneqConstDeriv(t, fx, fu, c, d);
+    copy(c, C, NG * NX);
+    copy(d, D, NG * NU);
+  }
+
+protected:
+  F f_;
+};
+// two inputs (pivoted LDLT / FullPivLU gain solve) and a time-varying inequality dimension; both pinned by golden
+// vectors of the reference's own FmpcSolver (oracle/ref/ref_fmpc.cpp)
+using FmpcProblemPlanarQuadrotor = FmpcProblemFromFunctor<nmpc_b200::models::PlanarQuadrotor<double>>;
+using FmpcProblemCartPoleWindowed = FmpcProblemFromFunctor<nmpc_b200::models::CartPoleWindowed<double>>;
 } // namespace oracle

@@ -29,6 +29,7 @@ namespace
 class FmpcProblemCartPole : public CartPoleBodies<nmpc_fmpc::FmpcProblem<4, 1, 4>>
 {
 public:
+  static constexpr bool kDynamicIneq = false;
   using CartPoleBodies<nmpc_fmpc::FmpcProblem<4, 1, 4>>::CartPoleBodies;
   IneqDimVector ineqConst(double, const StateDimVector & x, const InputDimVector & u) const override
   {
@@ -62,6 +63,7 @@ public:
 class FmpcProblemOscillator : public nmpc_fmpc::FmpcProblem<2, 1, 3>
 {
 public:
+  static constexpr bool kDynamicIneq = false;
   explicit FmpcProblemOscillator(const double * p) : FmpcProblem(p[0]) {}
   StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const override
   {
@@ -155,6 +157,205 @@ public:
   }
 };
 
+/** The planar quadrotor of include/nmpc_b200/models/planar_quadrotor.h (two inputs, four thrust limits) written as a
+    user of the reference would: an nmpc_fmpc::FmpcProblem<6, 2, 4> in Eigen idiom.  Not one of the reference's tests --
+    it exists to drive the n_u > 1 branch of FmpcSolver::backwardPass (LDLT / FullPivLU of G, FmpcSolver.hpp:596-617).
+    params: [dt, mass, inertia, arm, thrust_max, running_x[6], running_u, running_u_cross, terminal_x[6], ref_px, ref_pz]. */
+class FmpcProblemPlanarQuadrotor : public nmpc_fmpc::FmpcProblem<6, 2, 4>
+{
+public:
+  static constexpr bool kDynamicIneq = false;
+  explicit FmpcProblemPlanarQuadrotor(const double * p) : FmpcProblem(p[0])
+  {
+    mass_ = p[1];
+    inertia_ = p[2];
+    arm_ = p[3];
+    thrust_max_ = p[4];
+    for(int i = 0; i < 6; i++) running_x_[i] = p[5 + i];
+    running_u_ = p[11];
+    running_u_cross_ = p[12];
+    for(int i = 0; i < 6; i++) terminal_x_[i] = p[13 + i];
+    ref_.setZero();
+    ref_[0] = p[19];
+    ref_[1] = p[20];
+  }
+  double hover() const
+  {
+    return 0.5 * mass_ * 9.80665;
+  }
+  StateDimVector stateEq(double, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    const double st = std::sin(x[2]), ct = std::cos(x[2]);
+    const double thrust = u[0] + u[1];
+    StateDimVector x_dot;
+    x_dot << x[3], x[4], x[5], -1 * thrust * st / mass_, thrust * ct / mass_ - 9.80665, arm_ * (u[0] - u[1]) / inertia_;
+    return x + dt_ * x_dot;
+  }
+  double runningCost(double, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    double sx = 0;
+    for(int i = 0; i < 6; i++)
+    {
+      const double e = x[i] - ref_[i];
+      sx += running_x_[i] * (e * e);
+    }
+    const double e0 = u[0] - hover(), e1 = u[1] - hover();
+    const double su = running_u_ * (e0 * e0 + e1 * e1);
+    return (0.5 * sx + 0.5 * su) + running_u_cross_ * (e0 * e1);
+  }
+  double terminalCost(double, const StateDimVector & x) const override
+  {
+    double sx = 0;
+    for(int i = 0; i < 6; i++)
+    {
+      const double e = x[i] - ref_[i];
+      sx += terminal_x_[i] * (e * e);
+    }
+    return 0.5 * sx;
+  }
+  IneqDimVector ineqConst(double, const StateDimVector &, const InputDimVector & u) const override
+  {
+    IneqDimVector g;
+    g << -1 * u[0], u[0] - thrust_max_, -1 * u[1], u[1] - thrust_max_;
+    return g;
+  }
+  void calcStateEqDeriv(double,
+                        const StateDimVector & x,
+                        const InputDimVector & u,
+                        Eigen::Ref<StateStateDimMatrix> state_eq_deriv_x,
+                        Eigen::Ref<StateInputDimMatrix> state_eq_deriv_u) const override
+  {
+    const double st = std::sin(x[2]), ct = std::cos(x[2]);
+    const double thrust = u[0] + u[1];
+    state_eq_deriv_x.setZero();
+    state_eq_deriv_x(0, 3) = 1;
+    state_eq_deriv_x(1, 4) = 1;
+    state_eq_deriv_x(2, 5) = 1;
+    state_eq_deriv_x(3, 2) = -1 * thrust * ct / mass_;
+    state_eq_deriv_x(4, 2) = -1 * thrust * st / mass_;
+    state_eq_deriv_x *= dt_;
+    state_eq_deriv_x.diagonal().array() += 1;
+    state_eq_deriv_u.setZero();
+    state_eq_deriv_u(3, 0) = -1 * st / mass_;
+    state_eq_deriv_u(3, 1) = -1 * st / mass_;
+    state_eq_deriv_u(4, 0) = ct / mass_;
+    state_eq_deriv_u(4, 1) = ct / mass_;
+    state_eq_deriv_u(5, 0) = arm_ / inertia_;
+    state_eq_deriv_u(5, 1) = -1 * arm_ / inertia_;
+    state_eq_deriv_u *= dt_;
+  }
+  void calcRunningCostDeriv(double,
+                            const StateDimVector & x,
+                            const InputDimVector & u,
+                            Eigen::Ref<StateDimVector> running_cost_deriv_x,
+                            Eigen::Ref<InputDimVector> running_cost_deriv_u) const override
+  {
+    for(int i = 0; i < 6; i++) running_cost_deriv_x[i] = running_x_[i] * (x[i] - ref_[i]);
+    const double e0 = u[0] - hover(), e1 = u[1] - hover();
+    running_cost_deriv_u[0] = running_u_ * e0 + running_u_cross_ * e1;
+    running_cost_deriv_u[1] = running_u_ * e1 + running_u_cross_ * e0;
+  }
+  void calcRunningCostDeriv(double t,
+                            const StateDimVector & x,
+                            const InputDimVector & u,
+                            Eigen::Ref<StateDimVector> running_cost_deriv_x,
+                            Eigen::Ref<InputDimVector> running_cost_deriv_u,
+                            Eigen::Ref<StateStateDimMatrix> running_cost_deriv_xx,
+                            Eigen::Ref<InputInputDimMatrix> running_cost_deriv_uu,
+                            Eigen::Ref<StateInputDimMatrix> running_cost_deriv_xu) const override
+  {
+    calcRunningCostDeriv(t, x, u, running_cost_deriv_x, running_cost_deriv_u);
+    running_cost_deriv_xx.setZero();
+    for(int i = 0; i < 6; i++) running_cost_deriv_xx(i, i) = running_x_[i];
+    running_cost_deriv_uu(0, 0) = running_u_;
+    running_cost_deriv_uu(1, 1) = running_u_;
+    running_cost_deriv_uu(0, 1) = running_u_cross_;
+    running_cost_deriv_uu(1, 0) = running_u_cross_;
+    running_cost_deriv_xu.setZero();
+  }
+  void calcTerminalCostDeriv(double, const StateDimVector & x, Eigen::Ref<StateDimVector> terminal_cost_deriv_x)
+      const override
+  {
+    for(int i = 0; i < 6; i++) terminal_cost_deriv_x[i] = terminal_x_[i] * (x[i] - ref_[i]);
+  }
+  void calcTerminalCostDeriv(double t,
+                             const StateDimVector & x,
+                             Eigen::Ref<StateDimVector> terminal_cost_deriv_x,
+                             Eigen::Ref<StateStateDimMatrix> terminal_cost_deriv_xx) const override
+  {
+    calcTerminalCostDeriv(t, x, terminal_cost_deriv_x);
+    terminal_cost_deriv_xx.setZero();
+    for(int i = 0; i < 6; i++) terminal_cost_deriv_xx(i, i) = terminal_x_[i];
+  }
+  void calcIneqConstDeriv(double,
+                          const StateDimVector &,
+                          const InputDimVector &,
+                          Eigen::Ref<IneqStateDimMatrix> ineq_const_deriv_x,
+                          Eigen::Ref<IneqInputDimMatrix> ineq_const_deriv_u) const override
+  {
+    ineq_const_deriv_x.setZero();
+    ineq_const_deriv_u.setZero();
+    ineq_const_deriv_u(0, 0) = -1;
+    ineq_const_deriv_u(1, 0) = 1;
+    ineq_const_deriv_u(2, 1) = -1;
+    ineq_const_deriv_u(3, 1) = 1;
+  }
+
+protected:
+  double mass_, inertia_, arm_, thrust_max_, running_x_[6], running_u_, running_u_cross_, terminal_x_[6];
+  StateDimVector ref_;
+};
+
+/** Cart-pole whose position limits exist only for window_start <= t < window_end: the reference's DYNAMIC inequality
+    dimension, nmpc_fmpc::FmpcProblem<4, 1, Eigen::Dynamic> with ineqDim(t) overridden (FmpcProblem.h:62-86).
+    params: the cart-pole's 14, then [window_start, window_end]. */
+class FmpcProblemCartPoleWindowed : public CartPoleBodies<nmpc_fmpc::FmpcProblem<4, 1, Eigen::Dynamic>>
+{
+public:
+  using Base = CartPoleBodies<nmpc_fmpc::FmpcProblem<4, 1, Eigen::Dynamic>>;
+  static constexpr bool kDynamicIneq = true;
+  explicit FmpcProblemCartPoleWindowed(const double * p) : Base(p), window_start_(p[14]), window_end_(p[15]) {}
+  int ineqDim(double t) const override
+  {
+    return (t >= window_start_ && t < window_end_) ? 4 : 2;
+  }
+  IneqDimVector ineqConst(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    constexpr double u_max = 15.0;
+    constexpr double u_min = -1 * u_max;
+    constexpr double x_max = 20.0;
+    constexpr double x_min = -20.0;
+    IneqDimVector g(ineqDim(t));
+    g[0] = -1 * u[0] + u_min;
+    g[1] = u[0] - u_max;
+    if(ineqDim(t) == 4)
+    {
+      g[2] = -1 * x[0] + x_min;
+      g[3] = x[0] - x_max;
+    }
+    return g;
+  }
+  void calcIneqConstDeriv(double t,
+                          const StateDimVector &,
+                          const InputDimVector &,
+                          Eigen::Ref<IneqStateDimMatrix> ineq_const_deriv_x,
+                          Eigen::Ref<IneqInputDimMatrix> ineq_const_deriv_u) const override
+  {
+    ineq_const_deriv_x.setZero();
+    ineq_const_deriv_u.setZero();
+    ineq_const_deriv_u(0, 0) = -1;
+    ineq_const_deriv_u(1, 0) = 1;
+    if(ineqDim(t) == 4)
+    {
+      ineq_const_deriv_x(2, 0) = -1;
+      ineq_const_deriv_x(3, 0) = 1;
+    }
+  }
+
+protected:
+  double window_start_, window_end_;
+};
+
 template<class Problem, int NX, int NU, int NG>
 int fmpcSolve(const double * params,
                      const ref_fmpc_config * cfg,
@@ -175,7 +376,9 @@ int fmpcSolve(const double * params,
                      int * n_trace_out,
                      int * status_out)
 {
-  using Solver = nmpc_fmpc::FmpcSolver<NX, NU, NG>;
+  // NGS: the solver's inequality template parameter (NG, or Eigen::Dynamic with NG the padded width of the I/O arrays)
+  constexpr int NGS = Problem::kDynamicIneq ? Eigen::Dynamic : NG;
+  using Solver = nmpc_fmpc::FmpcSolver<NX, NU, NGS>;
   auto problem = std::make_shared<Problem>(params);
   Solver solver(problem);
   auto & c = solver.config();
@@ -200,7 +403,13 @@ int fmpcSolve(const double * params,
   for(int i = 0; i < N; i++)
   {
     for(int d = 0; d < NU; d++) var.u_list[i][d] = u_in[i * NU + d];
-    for(int d = 0; d < NG; d++)
+    const int ng_i = problem->ineqDim(t0 + i * problem->dt());
+    if constexpr(Problem::kDynamicIneq)
+    {
+      var.s_list[i].resize(ng_i);
+      var.nu_list[i].resize(ng_i);
+    }
+    for(int d = 0; d < ng_i; d++)
     {
       var.s_list[i][d] = s_in[i * NG + d];
       var.nu_list[i][d] = nu_in[i * NG + d];
@@ -229,8 +438,10 @@ int fmpcSolve(const double * params,
     for(int d = 0; d < NU; d++) u_out[i * NU + d] = v.u_list[i][d];
     for(int d = 0; d < NG; d++)
     {
-      s_out[i * NG + d] = v.s_list[i][d];
-      nu_out[i * NG + d] = v.nu_list[i][d];
+      // rows beyond a step's dimension do not exist in the reference: reported as the neutral (s, nu) = (1, 0)
+      const bool real = d < (int)v.s_list[i].size();
+      s_out[i * NG + d] = real ? v.s_list[i][d] : 1.0;
+      nu_out[i * NG + d] = real ? v.nu_list[i][d] : 0.0;
     }
     if(solver.traceDataList().size() > 0 && status != Solver::Status::Succeeded)
       for(int a = 0; a < NU; a++)
@@ -277,6 +488,14 @@ int ref_fmpc_solve(const char * model,
     return fmpcSolve<FmpcProblemOscillator, 2, 1, 3>(params, cfg, t0, x0, x_in, u_in, lambda_in, s_in, nu_in, x_out,
                                                      u_out, lambda_out, s_out, nu_out, K_out, kkt_out, n_trace_out,
                                                      status_out);
+  if(m == "fmpc_planar_quadrotor")
+    return fmpcSolve<FmpcProblemPlanarQuadrotor, 6, 2, 4>(params, cfg, t0, x0, x_in, u_in, lambda_in, s_in, nu_in, x_out,
+                                                          u_out, lambda_out, s_out, nu_out, K_out, kkt_out, n_trace_out,
+                                                          status_out);
+  if(m == "fmpc_cartpole_windowed")
+    return fmpcSolve<FmpcProblemCartPoleWindowed, 4, 1, 4>(params, cfg, t0, x0, x_in, u_in, lambda_in, s_in, nu_in, x_out,
+                                                           u_out, lambda_out, s_out, nu_out, K_out, kkt_out, n_trace_out,
+                                                           status_out);
   return -2;
 }
 
