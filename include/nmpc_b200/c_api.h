@@ -193,6 +193,15 @@ extern "C"
       launch, so the durations of an iteration are those of the whole batch.  *rows_filled = entries available. */
   int nmpc_b200_ddp_get_iteration_durations(nmpc_b200_ddp * h, double * ms, int rows, int * rows_filled);
 
+  /* ------------------------------------------------------------------- user functors ---- */
+
+  /** Load a shared library that registers problem functors (include/nmpc_b200/plugin.h: a .cu file with
+      NMPC_B200_REGISTER_DDP_MODEL / _FMPC_MODEL lines, built against this library).  The reference binds any
+      std::shared_ptr<DDPProblem> at run time (DDPSolver.h:255, FmpcSolver.h:296); this is the device-side equivalent:
+      after the call the plugin's functors can be named in nmpc_b200_ddp_create / nmpc_b200_fmpc_create.  Loading the
+      same path twice is harmless.  NMPC_B200_ERR_RUNTIME with the loader's message when the library cannot be loaded. */
+  int nmpc_b200_load_plugin(const char * path);
+
   /* ------------------------------------------------------- receding-horizon (MPC) loop ---- */
 
   /** The MPC loops that call the solvers in the reference (TestDDPBipedal.cpp:243-268,

@@ -12,8 +12,8 @@
  *   FullPivLU  complete pivoting (first maximum of |a| in column-major order of the trailing block), in-place
  *              elimination; solve() keeps the leading `rank` pivots, rank = #{|pivot| > eps * n * max|pivot|}, and
  *              sets the other solution components to zero.
- * The same restatement is in oracle/fmpc_oracle.hpp (LdltFactor, FullPivLuFactor) and in the Eigen stand-in the
- * reference headers are compiled against (oracle/ref/eigen_shim).  n is a small compile-time constant; the pivot
+ * Pinned by tests/test_fmpc_extra.py against golden vectors of the reference's own FmpcSolver<6, 2, 4> (both the
+ * LDLT and the FullPivLU branch).  n is a small compile-time constant; the pivot
  * permutations make the arrays dynamically indexed (local memory) -- only problems with n_u > 1 pay for it.
  */
 #pragma once

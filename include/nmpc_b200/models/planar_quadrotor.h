@@ -13,8 +13,8 @@
  * input CROSS weight (Luu = [[w, c], [c, w]]: w = 0, c != 0 and zero multipliers give the indefinite, zero-diagonal
  * G that makes LDLT report NumericalIssue), and 0 <= T_a <= thrust_max as g = (-T1, T1 - max, -T2, T2 - max) <= 0.
  * Method names and argument order follow nmpc_ddp::DDPProblem / nmpc_fmpc::FmpcProblem (DDPProblem.h:99-198,
- * FmpcProblem.h:94-107).  The same problem in Eigen idiom drives the reference's own FmpcSolver<6, 2, 4> in
- * oracle/ref/ref_fmpc.cpp (golden vectors of tests/test_fmpc_multi_input.py).
+ * FmpcProblem.h:94-107).  The same problem in Eigen idiom drives the reference's own FmpcSolver<6, 2, 4> for the golden
+ * vectors of tests/test_fmpc_extra.py.
  *
  * Flat parameters: [dt, mass, inertia, arm, thrust_max, running_x[6], running_u, running_u_cross, terminal_x[6],
  *                   ref_px, ref_pz]

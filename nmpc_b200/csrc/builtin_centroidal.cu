@@ -2,6 +2,6 @@
    (TestDDPCentroidalMotion.cpp), padded to NU = 16. */
 #include <nmpc_b200/models/centroidal_motion.h>
 
-#include "register.cuh"
+#include <nmpc_b200/engine/register.cuh>
 
 NMPC_B200_REGISTER_DDP_MODEL("centroidal_motion", nmpc_b200::models::CentroidalMotion<double>);

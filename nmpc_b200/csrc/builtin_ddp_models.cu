@@ -2,7 +2,7 @@
 #include <nmpc_b200/models/bipedal.h>
 #include <nmpc_b200/models/cartpole.h>
 
-#include "register.cuh"
+#include <nmpc_b200/engine/register.cuh>
 
 NMPC_B200_REGISTER_DDP_MODEL("cartpole", nmpc_b200::models::CartPole<double>);
 NMPC_B200_REGISTER_DDP_MODEL("bipedal", nmpc_b200::models::Bipedal<double>);

@@ -3,7 +3,7 @@
 #include <nmpc_b200/models/oscillator.h>
 #include <nmpc_b200/models/planar_quadrotor.h>
 
-#include "register.cuh"
+#include <nmpc_b200/engine/register.cuh>
 
 NMPC_B200_REGISTER_FMPC_MODEL("cartpole", nmpc_b200::models::CartPole<double>);
 NMPC_B200_REGISTER_FMPC_MODEL("oscillator", nmpc_b200::models::Oscillator<double>);

@@ -2,6 +2,6 @@
    forces; TestDDPVerticalMotion.cpp), padded to NU = 2. */
 #include <nmpc_b200/models/vertical_motion.h>
 
-#include "register.cuh"
+#include <nmpc_b200/engine/register.cuh>
 
 NMPC_B200_REGISTER_DDP_MODEL("vertical_motion", nmpc_b200::models::VerticalMotion<double>);

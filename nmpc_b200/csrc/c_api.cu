@@ -7,8 +7,10 @@
 #include <memory>
 #include <string>
 
-#include "common.cuh"
-#include "registry.h"
+#include <dlfcn.h>
+
+#include <nmpc_b200/engine/common.cuh>
+#include <nmpc_b200/engine/registry.h>
 
 struct nmpc_b200_ddp
 {
@@ -360,6 +362,20 @@ int nmpc_b200_ddp_get_durations(nmpc_b200_ddp * h, double * ms, int * launches)
     NMPC_REQUIRE_HANDLE(h);
     if(ms == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null output");
     h->engine->getDurations(ms, launches);
+  });
+}
+
+int nmpc_b200_load_plugin(const char * path)
+{
+  return guarded([&] {
+    if(path == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null plugin path");
+    // RTLD_GLOBAL is not needed: the plugin's registrars call registryEntry() of THIS library when its statics run
+    void * handle = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if(handle == nullptr)
+    {
+      const char * msg = dlerror();
+      throw Error(NMPC_B200_ERR_RUNTIME, std::string("cannot load plugin '") + path + "': " + (msg ? msg : "unknown error"));
+    }
   });
 }
 

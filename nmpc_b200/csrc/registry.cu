@@ -1,5 +1,5 @@
 /* nmpc_b200 -- functor registry storage. */
-#include "registry.h"
+#include <nmpc_b200/engine/registry.h>
 
 #include <map>
 #include <mutex>
