@@ -142,6 +142,11 @@ extern "C"
       input_limits_func_(current_t + i dt) (DDPSolver.hpp:470) for i = 0 .. horizon_steps-1, lower / upper
       [n_steps][NU] (host).  To be given again before a solve with another current_t or horizon. */
   int nmpc_b200_ddp_set_input_limits_horizon(nmpc_b200_ddp * h, int n_steps, const double * lower, const double * upper);
+  /** The same for the device-resident MPC loop (nmpc_b200_ddp_run_mpc), where the reference evaluates
+      input_limits_func_ anew at every solve (DDPSolver.hpp:470): lower / upper [n_ticks][n_steps][NU] (host) =
+      input_limits_func_(current_t + tick * tick_dt + i dt).  Needed only when the limits depend on time; run_mpc with
+      n_ticks beyond the table (or without one) answers NMPC_B200_ERR_UNSUPPORTED for such limits. */
+  int nmpc_b200_ddp_set_input_limits_mpc(nmpc_b200_ddp * h, int n_ticks, int n_steps, const double * lower, const double * upper);
 
   /** DDPSolver::solve(current_t, current_x, initial_u_list) (DDPSolver.hpp:27-141) for B <= capacity
       independent instances: x0[B][NX], u_init[B][N][NU].  n_u_steps must equal horizon_steps
@@ -214,7 +219,7 @@ extern "C"
         shift_inputs = 1   initial_u_list <- u_list[1:], last entry repeated  (TestDDPBipedal.cpp:265-267)
         shift_inputs = 0   initial_u_list <- u_list                           (TestDDPCartPole.cpp:395)
         clamp_u0 = 1       the applied input is u_list[0] clamped to the input limits (TestDDPCartPole.cpp:393-394;
-                           needs nmpc_b200_ddp_set_input_limits)
+                           needs nmpc_b200_ddp_set_input_limits, or _set_input_limits_mpc for limits that depend on time)
       current_t advances by tick_dt per tick. */
   typedef struct
   {

@@ -143,7 +143,6 @@ __global__ void __launch_bounds__(64) backward_fused_kernel(const __grid_constan
   using L = BlockLayout<M::NX, M::NU>;
   constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ int again;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   S * ring = reinterpret_cast<S *>(smem_raw);
@@ -172,53 +171,47 @@ __global__ void __launch_bounds__(64) backward_fused_kernel(const __grid_constan
   const S * xs = ws.x[sel];
   unsigned fill = 0;
 
-  if(warp == 1)
-  {
-    // ------------------------------------------------------------------ producer
-    while(true)
-    {
-      produceSweep<M>(model, ws, prm, b, lane, xs, us, ring, full, empty, fill);
-      __syncthreads(); // the consumer has decided whether lambda must grow and the sweep be repeated
-      if(!again) break;
-    }
-    return;
-  }
-
-  // -------------------------------------------------------------------- consumer
-  S lambda = live ? ws.lambda[b] : S(0);
-  S dlambda = live ? ws.dlambda[b] : S(0);
-  int n_bwd = live ? ws.n_bwd[b] : 0;
+  // warp 1 produces, warp 0 consumes; both meet at ONE barrier after every sweep, where the consumer's lanes vote on
+  // whether lambda must grow and the sweep be repeated
+  S lambda = (warp == 0 && live) ? ws.lambda[b] : S(0);
+  S dlambda = (warp == 0 && live) ? ws.dlambda[b] : S(0);
+  int n_bwd = (warp == 0 && live) ? ws.n_bwd[b] : 0;
   S dV0 = S(0), dV1 = S(0), k_rel_norm = S(0);
-  bool need = live;
+  bool need = (warp == 0) && live;
   bool failed = false;
   ProducerFeed<S, L::SIZE, kFusedDepth> feed{ring, full, empty, fill, lane};
   while(true)
   {
-    if(need) n_bwd++;
-    const bool ok = backwardSweep<M, CONSTRAINED>(model, ws, prm, b, lane, us, xs, feed, need, lambda, dV0, dV1, k_rel_norm);
-    if(need)
+    if(warp == 1)
     {
-      if(ok)
+      produceSweep<M>(model, ws, prm, b, lane, xs, us, ring, full, empty, fill);
+    }
+    else
+    {
+      if(need) n_bwd++;
+      const bool ok = backwardSweep<M, CONSTRAINED>(model, ws, prm, b, lane, us, xs, feed, need, lambda, dV0, dV1, k_rel_norm);
+      if(need)
       {
-        need = false;
-      }
-      else
-      {
-        // increase lambda (:194-204)
-        dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
-        lambda = fmax(lambda * dlambda, prm.lambda_min);
-        if(lambda > prm.lambda_max)
+        if(ok)
         {
-          failed = true;
           need = false;
+        }
+        else
+        {
+          // increase lambda (:194-204)
+          dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
+          lambda = fmax(lambda * dlambda, prm.lambda_min);
+          if(lambda > prm.lambda_max)
+          {
+            failed = true;
+            need = false;
+          }
         }
       }
     }
-    const bool more = __any_sync(kFull, need);
-    if(lane == 0) again = more ? 1 : 0;
-    __syncthreads();
-    if(!more) break;
+    if(!__syncthreads_or(need ? 1 : 0)) break;
   }
+  if(warp == 1) return;
   if(!live) return;
   ws.n_bwd[b] = n_bwd;
   ws.lambda[b] = lambda;

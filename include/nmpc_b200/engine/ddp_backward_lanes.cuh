@@ -770,98 +770,92 @@ struct LaneSmem
   }
 };
 
-/** Producer warp p of P: linearises sweep after sweep until the consumers' vote says no instance of the tile needs
-    another one.  `fill` is the ring's running tile count (continues across calls). */
-template<class M, int P>
-__device__ __forceinline__ void laneBackwardProducer(const M & model_in_constant_bank,
-                                                     const Workspace<typename M::Scalar> & ws,
-                                                     const SolverParams<typename M::Scalar> & prm,
-                                                     const LaneSmem<M> & sm,
-                                                     int b,
-                                                     int t,
-                                                     int p,
-                                                     const typename M::Scalar * xs,
-                                                     const typename M::Scalar * us,
-                                                     unsigned & fill)
+enum LaneRole
 {
-  while(true)
-  {
-    produceSweepLanes<M, P>(model_in_constant_bank, ws, prm, b, t, p, xs, us, sm.ring, sm.full, sm.empty, fill);
-    fill += (unsigned)prm.N;
-    if(!__syncthreads_or(0)) break; // the consumers decide whether lambda must grow and the sweep be repeated
-  }
-}
+  kLaneConsumer = 0, //!< a lane of the sweep: instance t of the tile, column lane % G
+  kLaneProducer = 1, //!< linearises instance t for every P-th step
+  kLaneIdle = 2 //!< a warp of the CTA without a part in the backward pass (persistent tile kernel): votes only
+};
 
-/** A warp of the CTA without a role in the backward pass: takes part in the votes. */
-__device__ __forceinline__ void laneBackwardIdle(int N, unsigned & fill)
-{
-  while(true)
-  {
-    fill += (unsigned)N;
-    if(!__syncthreads_or(0)) break;
-  }
-}
-
-/** Consumer lane (instance t of the tile, column j): procOnce() Step 2 (:188-231) -- sweeps with growing lambda until
-    the factorisation succeeds, then the small-gradient termination test and the hand-over to the line search. */
-template<class M, bool CONSTRAINED, class XCH>
-__device__ __forceinline__ void laneBackwardConsumer(const M & model,
-                                                     const Workspace<typename M::Scalar> & ws,
-                                                     const SolverParams<typename M::Scalar> & prm,
-                                                     const LaneSmem<M> & sm,
-                                                     int b,
-                                                     int t,
-                                                     int lane,
-                                                     bool live,
-                                                     const typename M::Scalar * xs,
-                                                     int iter,
-                                                     unsigned & fill)
+/** procOnce() Steps 1-2 (:157-231) for one 32-instance tile, called by EVERY warp of the CTA with its role: sweeps with
+    growing lambda until the factorisation succeeds for every instance of the tile (the consumers vote after each sweep
+    -- ONE barrier instruction for all roles), then the small-gradient termination test and the hand-over to the line
+    search.  `fill` is the ring's running tile count (continues across calls). */
+template<class M, bool CONSTRAINED, int P, class XCH>
+__device__ __forceinline__ void laneBackward(const M & model_in_constant_bank,
+                                             const Workspace<typename M::Scalar> & ws,
+                                             const SolverParams<typename M::Scalar> & prm,
+                                             const LaneSmem<M> & sm,
+                                             int role,
+                                             int b,
+                                             int t,
+                                             int lane,
+                                             int p,
+                                             bool live,
+                                             const typename M::Scalar * xs,
+                                             const typename M::Scalar * us,
+                                             int iter,
+                                             unsigned & fill)
 {
   using S = typename M::Scalar;
   using LL = LaneLayout<M>;
   constexpr int NX = M::NX, G = LL::G;
-  const int j = lane % G; // this lane's column
+  const int j = lane % G; // consumer: this lane's column
   const int jj = (j < NX) ? j : (NX - 1); // idle lanes (n_x < G) shadow the last column and never store
   // two scratch arrays (strides: LaneLayout::strideFor)
   S * x1 = sm.scratch + (size_t)t * LL::X1S;
   S * x2 = sm.scratch + (size_t)kTile * LL::X1S + (size_t)t * LL::X2S;
-  S lambda = live ? ws.lambda[b] : S(0);
-  S dlambda = live ? ws.dlambda[b] : S(0);
-  int n_bwd = live ? ws.n_bwd[b] : 0;
+  const bool consumer = role == kLaneConsumer;
+  S lambda = (consumer && live) ? ws.lambda[b] : S(0);
+  S dlambda = (consumer && live) ? ws.dlambda[b] : S(0);
+  int n_bwd = (consumer && live) ? ws.n_bwd[b] : 0;
   S dV0 = S(0), dV1 = S(0), k_rel_norm = S(0);
-  bool need = live;
+  bool need = consumer && live;
   bool failed = false;
 
   while(true)
   {
-    if(need) n_bwd++;
-    const bool ok = (prm.reg_type == 2) ? laneSweep<M, CONSTRAINED, true, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1, x2,
-                                                                               sm.full, sm.empty, fill, need, lambda, dV0, dV1,
-                                                                               k_rel_norm)
-                                        : laneSweep<M, CONSTRAINED, false, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1,
-                                                                                x2, sm.full, sm.empty, fill, need, lambda, dV0, dV1,
-                                                                                k_rel_norm);
-    if(need)
+    if(role == kLaneProducer)
     {
-      if(ok)
+      produceSweepLanes<M, P>(model_in_constant_bank, ws, prm, b, t, p, xs, us, sm.ring, sm.full, sm.empty, fill);
+      fill += (unsigned)prm.N;
+    }
+    else if(role == kLaneIdle)
+    {
+      fill += (unsigned)prm.N;
+    }
+    else
+    {
+      const M model = model_in_constant_bank;
+      if(need) n_bwd++;
+      const bool ok = (prm.reg_type == 2)
+                          ? laneSweep<M, CONSTRAINED, true, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1, x2, sm.full,
+                                                                 sm.empty, fill, need, lambda, dV0, dV1, k_rel_norm)
+                          : laneSweep<M, CONSTRAINED, false, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1, x2, sm.full,
+                                                                  sm.empty, fill, need, lambda, dV0, dV1, k_rel_norm);
+      if(need)
       {
-        need = false;
-      }
-      else
-      {
-        // increase lambda (:194-204)
-        dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
-        lambda = fmax(lambda * dlambda, prm.lambda_min);
-        if(lambda > prm.lambda_max)
+        if(ok)
         {
-          failed = true;
           need = false;
+        }
+        else
+        {
+          // increase lambda (:194-204)
+          dlambda = fmax(dlambda * prm.lambda_factor, prm.lambda_factor);
+          lambda = fmax(lambda * dlambda, prm.lambda_min);
+          if(lambda > prm.lambda_max)
+          {
+            failed = true;
+            need = false;
+          }
         }
       }
     }
+    // does any instance of the tile need another sweep with a larger lambda?
     if(!__syncthreads_or(need ? 1 : 0)) break;
   }
-  if(!live || j != 0) return;
+  if(!consumer || !live || j != 0) return;
   ws.n_bwd[b] = n_bwd;
   ws.lambda[b] = lambda;
   ws.dlambda[b] = dlambda;
@@ -926,13 +920,8 @@ __global__ void __launch_bounds__((LaneLayout<M>::CW + P) * 32 * TPC)
   const S * us = ws.u[sel];
   const S * xs = ws.x[sel];
   unsigned fill = 0;
-  if(producer)
-    laneBackwardProducer<M, P>(model_in_constant_bank, ws, prm, sm, b, t, warp - CW, xs, us, fill);
-  else
-  {
-    const M model = model_in_constant_bank;
-    laneBackwardConsumer<M, CONSTRAINED, XCH>(model, ws, prm, sm, b, t, lane, live, xs, iter, fill);
-  }
+  laneBackward<M, CONSTRAINED, P, XCH>(model_in_constant_bank, ws, prm, sm, producer ? kLaneProducer : kLaneConsumer, b, t, lane,
+                                       warp - CW, live, xs, us, iter, fill);
 }
 } // namespace ddp
 } // namespace nmpc_b200

@@ -136,6 +136,7 @@ public:
       }
     setInputLimitsHorizon(N, lo.data(), hi.data());
     limits_vary_ = false;
+    mpc_limit_ticks_ = 0;
   }
 
   /** input_limits_func_(current_t + i dt) for i = 0 .. N-1 (DDPSolver.h:282-285, DDPSolver.hpp:470): lower / upper
@@ -164,6 +165,34 @@ public:
       NMPC_CUDA_CHECK(cudaMemcpy(d_u_hi_.ptr, hi.data(), sizeof(S) * hi.size(), cudaMemcpyHostToDevice));
     }
     have_limits_ = true;
+  }
+
+  /** input_limits_func_(current_t + tick * tick_dt + i dt) for every tick of the device-resident MPC loop and every
+      horizon step (DDPSolver.hpp:470 evaluates the function anew at every solve): lower / upper [n_ticks][n_steps][NU]. */
+  void setInputLimitsMpc(int n_ticks, int n_steps, const double * lower, const double * upper) override
+  {
+    DeviceGuard guard(device_);
+    const int N = cfg_.horizon_steps;
+    if(n_steps != N)
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "input limits are needed for " + std::to_string(N) + " steps but "
+                                                      + std::to_string(n_steps) + " were given");
+    if(n_ticks <= 0 || lower == nullptr || upper == nullptr)
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null or empty per-tick input limits");
+    const size_t n = (size_t)n_ticks * N * NU;
+    std::vector<S> lo(n), hi(n);
+    for(size_t e = 0; e < n; e++)
+    {
+      lo[e] = S(lower[e]);
+      hi[e] = S(upper[e]);
+    }
+    mpc_lo_.allocate(n > 0 ? n : 1);
+    mpc_hi_.allocate(n > 0 ? n : 1);
+    if(n > 0)
+    {
+      NMPC_CUDA_CHECK(cudaMemcpy(mpc_lo_.ptr, lo.data(), sizeof(S) * n, cudaMemcpyHostToDevice));
+      NMPC_CUDA_CHECK(cudaMemcpy(mpc_hi_.ptr, hi.data(), sizeof(S) * n, cudaMemcpyHostToDevice));
+    }
+    mpc_limit_ticks_ = n_ticks;
   }
 
   void solve(int B, double current_t, const double * x0, const double * u_init, int n_u_steps, bool on_device, void * stream)
@@ -198,10 +227,12 @@ public:
       throw Error(NMPC_B200_ERR_UNSUPPORTED, "plant = 1 needs a functor with stateEq(t, x, u, dt)");
     if(mpc.plant == 1 && mpc.n_substeps <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "n_substeps must be positive");
     if(mpc.clamp_u0 && !have_limits_) throw Error(NMPC_B200_ERR_RUNTIME, "clamp_u0 is set but no input limits were given");
-    if(limits_vary_ && (mpc.clamp_u0 || cfg_.with_input_constraint))
+    const bool needs_limits = mpc.clamp_u0 || cfg_.with_input_constraint;
+    const bool per_tick_limits = needs_limits && mpc_limit_ticks_ >= mpc.n_ticks;
+    if(limits_vary_ && needs_limits && !per_tick_limits)
       throw Error(NMPC_B200_ERR_UNSUPPORTED,
-                  "the device-resident MPC loop needs input limits that are constant over time (the limits of a "
-                  "horizon are given per step index, and the loop shifts the horizon every tick)");
+                  "the input limits change along the horizon, so every tick of the device-resident MPC loop needs its own "
+                  "table: give them with nmpc_b200_ddp_set_input_limits_mpc for at least n_ticks ticks");
     cudaStream_t st = beginSolve(B, n_u_steps, x0, u_init, stream);
     const size_t T = mpc.n_ticks;
     const size_t Bp = Bp_;
@@ -233,10 +264,18 @@ public:
         record(st);
         record(st);
       }
+      if(per_tick_limits)
+      {
+        // this tick's horizon: input_limits_func_(t + i dt), i = 0 .. N-1 (the clamp of the applied input reads step 0)
+        ws_.u_lo = mpc_lo_.ptr + (size_t)tick * cfg_.horizon_steps * NU;
+        ws_.u_hi = mpc_hi_.ptr + (size_t)tick * cfg_.horizon_steps * NU;
+      }
       runIterations(B, t, st);
       mpc_advance_kernel<M><<<(B + 127) / 128, 128, 0, st>>>(model_, ws_, prm_, mp, logs, tick, S(t));
       NMPC_CUDA_CHECK(cudaGetLastError());
     }
+    ws_.u_lo = d_u_lo_.ptr;
+    ws_.u_hi = d_u_hi_.ptr;
     // logs back to instance-major
     auto out_f64 = [&](const S * src, double * dst, int R) {
       if(dst == nullptr) return;
@@ -1184,7 +1223,8 @@ protected:
   cudaStream_t last_stream_ = nullptr;
   DeviceBuffer<S> x_[2], u_[2], cost_[2], deriv_, vterm_, kff_, kfb_, trace_, scal_, d_u_lo_, d_u_hi_;
   DeviceBuffer<int> ints_, d_counter_, d_fan_count_, fan_ints_;
-  DeviceBuffer<S> fan_scratch_, mpc_x_, mpc_u_;
+  DeviceBuffer<S> fan_scratch_, mpc_x_, mpc_u_, mpc_lo_, mpc_hi_;
+  int mpc_limit_ticks_ = 0; //!< ticks covered by the per-tick limit tables (setInputLimitsMpc)
   DeviceBuffer<int> mpc_i_;
   FwdFanout<S> fan_{};
   DeviceBuffer<double> stage_in_x_, stage_in_u_, stage_out_;

@@ -526,7 +526,16 @@ __device__ __forceinline__ void mbarArrive(unsigned long long * bar)
 __device__ __forceinline__ void cpAsyncArriveOn(unsigned long long * bar)
 {
   const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+#ifdef NMPC_B200_LOADER_WAITS
+  // diagnostic build (tools/sanitize_cases.py, profiles/r2_sanitizer.md): the loader waits for its copies and arrives
+  // itself.  compute-sanitizer's racecheck follows an ordinary mbarrier arrive but not the arrive that the hardware
+  // performs when a thread's cp.async operations complete; with this build its cp.async hazards disappear while the
+  // results stay bit-identical -- i.e. they are a limitation of the tool, not races.
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
+#else
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
+#endif
 }
 
 /** Loader side: rows 0 .. ROWS-1 of `n_fills` consecutive steps.  row_ptr[r] = address of this lane's element of row r

@@ -70,8 +70,9 @@ __global__ void mpc_advance_kernel(const __grid_constant__ M model,
   const size_t Bp = ws.Bp;
   const int N = prm.N;
   const int sel = ws.sel[b];
-  const S * __restrict__ xs = ws.x[sel];
-  const S * __restrict__ us = ws.u[sel];
+  // no __restrict__: with sel == 0 the warm-start shift below reads and writes the same buffer
+  const S * xs = ws.x[sel];
+  const S * us = ws.u[sel];
 
   Matrix<S, NX, 1> x;
   Matrix<S, NU, 1> u;
@@ -121,7 +122,7 @@ __global__ void mpc_advance_kernel(const __grid_constant__ M model,
   }
 
   // warm start of the next solve; with sel == 0 the shift is in place (entry i+1 is read before entry i is written)
-  S * __restrict__ ud = ws.u[0];
+  S * ud = ws.u[0];
   if(mp.shift_inputs)
   {
     for(int i = 0; i + 1 < N; i++)

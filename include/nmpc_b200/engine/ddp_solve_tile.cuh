@@ -80,24 +80,13 @@ __device__ __noinline__ unsigned tileBackwardPhase(const M * model_p,
   const LaneSmem<M> sm_bwd(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if(warp < CW)
-  {
-    const M model = *model_p;
-    const int t = warp * IPW + lane / G;
-    const int b = tb + t;
-    const bool live = (b < ws.B) && (ws.status[b < ws.B ? b : 0] == 0);
-    const int sel = live ? ws.sel[b] : 0;
-    laneBackwardConsumer<M, CONSTRAINED, XCH>(model, ws, prm, sm_bwd, b, t, lane, live, ws.x[sel], iter, bwd_fill);
-  }
-  else if(warp < CW + P)
-  {
-    const int b = tb + lane;
-    const bool live = (b < ws.B) && (ws.status[b < ws.B ? b : 0] == 0);
-    const int sel = live ? ws.sel[b] : 0;
-    laneBackwardProducer<M, P>(*model_p, ws, prm, sm_bwd, b, lane, warp - CW, ws.x[sel], ws.u[sel], bwd_fill);
-  }
-  else
-    laneBackwardIdle(prm.N, bwd_fill);
+  const int role = (warp < CW) ? kLaneConsumer : (warp < CW + P ? kLaneProducer : kLaneIdle);
+  const int t = (role == kLaneConsumer) ? warp * IPW + lane / G : lane;
+  const int b = tb + t;
+  const bool live = (b < ws.B) && (ws.status[b < ws.B ? b : 0] == 0);
+  const int sel = live ? ws.sel[b] : 0;
+  laneBackward<M, CONSTRAINED, P, XCH>(*model_p, ws, prm, sm_bwd, role, b, t, lane, warp - CW, live, ws.x[sel], ws.u[sel], iter,
+                                       bwd_fill);
   return bwd_fill;
 }
 

@@ -27,6 +27,7 @@ public:
   virtual const nmpc_b200_ddp_config & config() const = 0;
   virtual void setInputLimits(const double * lower, const double * upper) = 0;
   virtual void setInputLimitsHorizon(int n_steps, const double * lower, const double * upper) = 0;
+  virtual void setInputLimitsMpc(int n_ticks, int n_steps, const double * lower, const double * upper) = 0;
   virtual void solve(int B,
                      double current_t,
                      const double * x0,

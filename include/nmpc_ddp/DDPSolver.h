@@ -212,10 +212,38 @@ public:
               int * status_log = nullptr)
   {
     ensureHandle();
-    if(config_.with_input_constraint || mpc.clamp_u0) applyInputLimits(current_t);
+    if(config_.with_input_constraint || mpc.clamp_u0)
+    {
+      applyInputLimits(current_t);
+      applyInputLimitsMpc(current_t, mpc);
+    }
     nmpc_b200::throwOnError(nmpc_b200_ddp_run_mpc(handle_, B, current_t, x0, u_init, n_steps, &mpc, x_log, u_log,
                                                   iters_log, status_log, 0, nullptr));
     last_B_ = B;
+  }
+
+  /** input_limits_func_ at every (tick, horizon step) time of the loop, as the reference evaluates it at every
+      solve (DDPSolver.hpp:470); uploaded only when it actually depends on time. */
+  void applyInputLimitsMpc(double current_t, const nmpc_b200_mpc_config & mpc)
+  {
+    const int N = config_.horizon_steps;
+    const size_t per_tick = static_cast<size_t>(N) * (InputDim > 0 ? InputDim : 1);
+    std::vector<double> lo(per_tick * mpc.n_ticks), hi(per_tick * mpc.n_ticks);
+    bool varies = false;
+    for(int k = 0; k < mpc.n_ticks; k++)
+      for(int i = 0; i < N; i++)
+      {
+        const auto limits = input_limits_func_(current_t + k * mpc.tick_dt + i * problem_->dt());
+        for(int d = 0; d < InputDim; d++)
+        {
+          const size_t e = k * per_tick + static_cast<size_t>(i) * InputDim + d;
+          lo[e] = limits[0][d];
+          hi[e] = limits[1][d];
+          if(lo[e] != lo[d] || hi[e] != hi[d]) varies = true;
+        }
+      }
+    if(varies)
+      nmpc_b200::throwOnError(nmpc_b200_ddp_set_input_limits_mpc(handle_, mpc.n_ticks, N, lo.data(), hi.data()));
   }
 
   /** \brief Copy a result field of the last solveBatch() (see nmpc_b200_ddp_field). */

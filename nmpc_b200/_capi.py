@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "nmpc_b200_ddp_get_config", "nmpc_b200_ddp_set_input_limits", "nmpc_b200_ddp_set_input_limits_horizon",
     "nmpc_b200_ddp_solve", "nmpc_b200_ddp_get",
     "nmpc_b200_ddp_sync", "nmpc_b200_ddp_enable_timing", "nmpc_b200_ddp_get_durations", "nmpc_b200_ddp_run_mpc",
-    "nmpc_b200_ddp_get_iteration_durations", "nmpc_b200_load_plugin",
+    "nmpc_b200_ddp_get_iteration_durations", "nmpc_b200_load_plugin", "nmpc_b200_ddp_set_input_limits_mpc",
     "nmpc_b200_fmpc_config_default", "nmpc_b200_fmpc_create", "nmpc_b200_fmpc_destroy", "nmpc_b200_fmpc_set_config",
     "nmpc_b200_fmpc_solve", "nmpc_b200_fmpc_get", "nmpc_b200_fmpc_sync", "nmpc_b200_fmpc_enable_timing",
     "nmpc_b200_fmpc_get_durations", "nmpc_b200_fmpc_run_mpc",
@@ -130,6 +130,7 @@ def lib():
         L.nmpc_b200_ddp_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.nmpc_b200_ddp_get_durations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.nmpc_b200_load_plugin.argtypes = [C.c_char_p]
+        L.nmpc_b200_ddp_set_input_limits_mpc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.nmpc_b200_ddp_get_iteration_durations.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.nmpc_b200_fmpc_solve.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 6 + [C.c_int, C.c_int,
                                                                                                   C.c_void_p]

@@ -295,6 +295,14 @@ int nmpc_b200_ddp_set_input_limits_horizon(nmpc_b200_ddp * h, int n_steps, const
   });
 }
 
+int nmpc_b200_ddp_set_input_limits_mpc(nmpc_b200_ddp * h, int n_ticks, int n_steps, const double * lower, const double * upper)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_HANDLE(h);
+    h->engine->setInputLimitsMpc(n_ticks, n_steps, lower, upper);
+  });
+}
+
 int nmpc_b200_ddp_solve(nmpc_b200_ddp * h,
                         int B,
                         double current_t,

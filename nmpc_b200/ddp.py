@@ -148,6 +148,23 @@ class DDPSolver:
         check(lib().nmpc_b200_ddp_set_input_limits_horizon(self._h, N, lo.ctypes.data_as(C.c_void_p),
                                                            hi.ctypes.data_as(C.c_void_p)))
 
+    def _apply_limits_mpc(self, current_t, n_ticks, tick_dt):
+        """A limits callable at every (tick, horizon step) time of the device-resident MPC loop (the reference
+        evaluates input_limits_func_ at every solve, DDPSolver.hpp:470); uploaded only when it depends on time."""
+        func = getattr(self, "_limits_func", None)
+        if func is None or n_ticks <= 0:
+            return
+        N = self._config.horizon_steps
+        dt = float(self.params[0])
+        lo, hi = np.empty((n_ticks, N, self.nu)), np.empty((n_ticks, N, self.nu))
+        for k in range(n_ticks):
+            for i in range(N):
+                l, h = func(current_t + k * tick_dt + i * dt)
+                lo[k, i], hi[k, i] = np.asarray(l, dtype=np.float64).reshape(self.nu), np.asarray(h, dtype=np.float64).reshape(self.nu)
+        if np.any(lo != lo[0, 0]) or np.any(hi != hi[0, 0]):
+            check(lib().nmpc_b200_ddp_set_input_limits_mpc(self._h, n_ticks, N, lo.ctypes.data_as(C.c_void_p),
+                                                           hi.ctypes.data_as(C.c_void_p)))
+
     def solve(self, current_t, current_x, initial_u_list):
         """Single-instance ``solve`` (DDPSolver.hpp:27-141); returns True iff converged (retval == 1)."""
         u = np.asarray(initial_u_list, dtype=np.float64)
@@ -192,6 +209,7 @@ class DDPSolver:
         Returns a dict: x [B, n_ticks+1, NX], u [B, n_ticks, NU] (applied inputs), iters, status [B, n_ticks]."""
         self._apply_config()
         self._apply_limits(float(current_t))
+        self._apply_limits_mpc(float(current_t), int(n_ticks), float(tick_dt))
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         u_init = np.ascontiguousarray(u_init, dtype=np.float64)
         B = x0.shape[0]

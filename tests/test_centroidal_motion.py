@@ -262,3 +262,42 @@ def test_device_wide_sweep_agrees_with_the_cooperative_sweep_and_the_oracle(gpu,
         assert np.array_equal(out[tag][2], ref["iters"]) and np.array_equal(out[tag][4], ref["n_bwd"])
     # same expressions in the same order: the two device variants agree to the last bit
     assert np.array_equal(out["wide"][0], out["coop"][0]) and np.array_equal(out["wide"][3], out["coop"][3])
+
+
+@pytest.mark.gpu
+def test_device_with_input_limits_many_inputs(gpu):
+    """n_u = 16 WITH input limits (with_input_constraint: the cooperative K2 with the in-register BoxQP of 16 variables;
+    the reference's centroidal test is unconstrained, TestDDPCentroidalMotion.cpp:247).  Ridge forces in [0, f_max]:
+    the lower bound is active wherever the unconstrained solution would pull.  Against the oracle (whose BoxQP passes
+    the reference's known-answer tests): same iteration / backward-pass counts and status, trajectories and costs at
+    the M-ref tolerances over the first two iterations -- from then on an input sitting ON a bound makes the
+    clamped-set test an exact floating-point equality (BoxQP.h:189-191) -- and the bounds respected throughout."""
+    p = O.default_params("centroidal_motion")
+    B = 4
+    x0 = np.repeat(X0, B, axis=0)
+    x0[1:, :3] += np.random.default_rng(11).uniform(-0.05, 0.05, (B - 1, 3))
+    u_init = np.zeros((B, N, 16))
+    lo, hi = np.zeros(16), np.full(16, 40.0)
+    for max_iter in (1, 2, 6):
+        ref = O.ddp_solve_batch("centroidal_motion", p, O.ddp_config(max_iter=max_iter, horizon_steps=N, with_input_constraint=1),
+                                x0, u_init, u_lo=lo, u_hi=hi)
+        solver = gpu.DDPSolver("centroidal_motion", params=p, batch_capacity=B)
+        c = solver.config()
+        c.horizon_steps, c.max_iter, c.with_input_constraint = N, max_iter, True
+        solver.setInputLimitsFunc((lo, hi))
+        solver.solve_batch(0.0, x0, u_init)
+        u = solver.controlData().u_list
+        umax = np.abs(ref["u"]).max()
+        _record(f"boxqp_nu16_it{max_iter}", du_vs_oracle_rel=np.abs(u - ref["u"]).max() / umax,
+                dcost_vs_oracle_rel=np.abs(solver.cost() / ref["cost"] - 1).max(), iters_device=solver.iterations(),
+                iters_oracle=ref["iters"], clamped_fraction=float(np.mean(solver.K_list().reshape(B, N, 16, 9).any(axis=3) == 0)))
+        assert np.array_equal(solver.status(), ref["status"])
+        if max_iter <= 2:
+            assert np.array_equal(solver.iterations(), ref["iters"]) and np.array_equal(solver.n_backward(), ref["n_bwd"])
+            np.testing.assert_allclose(u, ref["u"], rtol=0, atol=1e-9 * umax)
+            np.testing.assert_allclose(solver.cost(), ref["cost"], rtol=1e-10, atol=0)
+        else:
+            np.testing.assert_allclose(solver.cost(), ref["cost"], rtol=1e-2, atol=0)
+        dims = np.array([input_dim(i * DT) for i in range(N)])
+        assert np.all(u[:, dims == 0] == 0.0)
+        solver.close()

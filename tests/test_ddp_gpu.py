@@ -378,7 +378,7 @@ def test_tiny_horizons(gpu, N):
 def test_input_limits_that_change_along_the_horizon(gpu):
     """setInputLimitsFunc with a genuine function of time (DDPSolver.h:282-285; evaluated at every t_i by backwardPass,
     DDPSolver.hpp:470): the limits tighten from +-15 N to +-3 N over the horizon.  Against the oracle driven with the
-    same table; the constant-limit call must keep working after it; the device MPC loop refuses time-varying limits."""
+    same table; the constant-limit call must keep working after it; the device MPC loop runs with such limits too."""
     p = O.default_params("cartpole")
     B, N, t0 = 48, 100, 0.3
     x0, u0 = O.cartpole_x0(B, 77), np.zeros((B, N, 1))
@@ -402,9 +402,9 @@ def test_input_limits_that_change_along_the_horizon(gpu):
     assert _rel_u(s.controlData().u_list, ref["u"]).max() <= U_TOL_REF
     assert np.max(np.abs(s.cost() - ref["cost"]) / np.abs(ref["cost"])) <= COST_TOL_REF
     k = s.k_list()[:, :, 0]  # the feedforward term respects each step's own box (lo_i - u_i <= k_i <= hi_i - u_i)
-    with pytest.raises(gpu.NmpcB200Error) as e:
-        s.run_mpc(t0, x0, u0, n_ticks=2, tick_dt=dt)
-    assert e.value.code == 7
+    # the device MPC loop takes such limits as per-tick tables (tests/test_mpc_gpu.py covers its results)
+    log = s.run_mpc(t0, x0, u0, n_ticks=2, tick_dt=dt)
+    assert np.isfinite(log["u"]).all()
     # constant limits afterwards: same result as a fresh solver
     s.setInputLimitsFunc((np.array([-15.0]), np.array([15.0])))
     s.solve_batch(0.0, x0, u0)

@@ -85,6 +85,61 @@ def test_cartpole_mpc_loop_simulated_plant(gpu):
     np.testing.assert_allclose(got["x"][:, ticks], x, rtol=0, atol=1e-8)
 
 
+def test_cartpole_mpc_loop_with_limits_that_depend_on_time(gpu):
+    """The same loop with input limits that are a genuine function of time (DDPSolver.h:282-285): the reference
+    evaluates input_limits_func_(t_i) at every solve (DDPSolver.hpp:470), so every tick of the device-resident loop has
+    its own limit table (nmpc_b200_ddp_set_input_limits_mpc); the clamp of the applied input uses the tick's time."""
+    p = O.default_params("cartpole")
+    N, B, ticks = 100, 4, 25
+    mpc_dt, sim_dt, dt = 0.004, 0.002, p[0]
+    x0 = np.concatenate([[[0.0, np.pi, 0.0, 0.0]], O.cartpole_x0(B - 1, 8)])
+    u0 = np.zeros((B, N, 1))
+
+    def limits(t):
+        w = 15.0 - 10.0 * min(max(t / 0.6, 0.0), 1.0)  # the band closes from +-15 N to (-5, 2.5) N within 0.6 s
+        return np.array([-w]), np.array([0.5 * w])
+
+    solver = gpu.DDPSolver("cartpole", params=p, batch_capacity=B)
+    c = solver.config()
+    c.horizon_steps, c.max_iter, c.with_input_constraint = N, 3, True
+    solver.setInputLimitsFunc(limits)
+    got = solver.run_mpc(0.0, x0, u0, n_ticks=ticks, tick_dt=mpc_dt, plant="sim", shift_inputs=False, clamp_u0=True,
+                         sim_dt=sim_dt, n_substeps=2)
+
+    cfg = O.ddp_config(horizon_steps=N, max_iter=3, with_input_constraint=1)
+    p_sim = p.copy()
+    p_sim[0] = sim_dt
+    t, x, u = 0.0, x0.copy(), u0.copy()
+    clamped = 0
+    for k in range(ticks):
+        lo = np.array([limits(t + i * dt)[0] for i in range(N)])
+        hi = np.array([limits(t + i * dt)[1] for i in range(N)])
+        r = O.ddp_solve_cartpole_tv_limits(p, cfg, x, u, lo, hi, t0=t)
+        ua = np.clip(r["u"][:, 0], lo[0], hi[0])
+        clamped += int(np.sum(ua != r["u"][:, 0]))
+        np.testing.assert_allclose(got["x"][:, k], x, rtol=0, atol=1e-8, err_msg=f"tick {k}")
+        np.testing.assert_allclose(got["u"][:, k], ua, rtol=0, atol=1e-7, err_msg=f"tick {k}")
+        assert np.array_equal(got["iters"][:, k], r["iters"]), f"tick {k}"
+        for _ in range(2):
+            x = np.stack([O.model_eval("cartpole", p_sim, t, x[b], ua[b])["x_next"] for b in range(B)])
+        t = (k + 1) * mpc_dt
+        u = r["u"].copy()
+    np.testing.assert_allclose(got["x"][:, ticks], x, rtol=0, atol=1e-8)
+    # without a per-tick table (the raw C entry point with limits that vary along the horizon) the loop still refuses
+    lo0 = np.array([limits(i * dt)[0] for i in range(N)])
+    hi0 = np.array([limits(i * dt)[1] for i in range(N)])
+    import ctypes as C
+
+    from nmpc_b200._capi import check, lib
+    check(lib().nmpc_b200_ddp_set_input_limits_horizon(solver._h, N, lo0.ctypes.data_as(C.c_void_p),
+                                                       hi0.ctypes.data_as(C.c_void_p)))
+    solver._limits_func = None
+    with pytest.raises(gpu.NmpcB200Error) as e:
+        solver.run_mpc(0.0, x0, u0, n_ticks=ticks + 5, tick_dt=mpc_dt, plant="sim", shift_inputs=False, clamp_u0=True,
+                       sim_dt=sim_dt, n_substeps=2)
+    assert e.value.code == 7
+
+
 def test_mpc_argument_errors(gpu):
     solver = gpu.DDPSolver("bipedal", batch_capacity=2)
     solver.config().horizon_steps = 20
