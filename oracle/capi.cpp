@@ -326,6 +326,11 @@ int oracle_model_dims(const char * model, int * nx, int * nu, int * ng, int * np
     *nx = 9, *nu = 16, *ng = 0, *nparams = DDPProblemCentroidalMotion::kNumParams;
     return 0;
   }
+  if(m == "planar_quadrotor")
+  {
+    *nx = 6, *nu = 2, *ng = 0, *nparams = DDPProblemPlanarQuadrotor::kNumParams;
+    return 0;
+  }
   if(m == "fmpc_cartpole")
   {
     *nx = 4, *nu = 1, *ng = 4, *nparams = FmpcProblemCartPole::kNumParams;
@@ -362,6 +367,8 @@ int oracle_model_default_params(const char * model, double * params)
     DDPProblemVerticalMotion::defaultParams(params);
   else if(m == "centroidal_motion")
     DDPProblemCentroidalMotion::defaultParams(params);
+  else if(m == "planar_quadrotor")
+    DDPProblemPlanarQuadrotor::defaultParams(params);
   else if(m == "fmpc_cartpole")
     FmpcProblemCartPole::defaultParams(params);
   else if(m == "fmpc_oscillator")
@@ -418,6 +425,10 @@ int oracle_ddp_solve_batch(const char * model,
     return ddpSolveBatch<DDPProblemCentroidalMotion, 9, 16>(params, cfg, B, t0, x0, u_init, u_lo, u_hi, x_out, u_out,
                                                             cost_out, k_out, K_out, trace_out, n_trace_out, status_out,
                                                             iters_out, n_fwd_out, n_bwd_out, nthreads);
+  if(m == "planar_quadrotor")
+    return ddpSolveBatch<DDPProblemPlanarQuadrotor, 6, 2>(params, cfg, B, t0, x0, u_init, u_lo, u_hi, x_out, u_out,
+                                                          cost_out, k_out, K_out, trace_out, n_trace_out, status_out,
+                                                          iters_out, n_fwd_out, n_bwd_out, nthreads);
   return -2;
 }
 
@@ -474,6 +485,9 @@ int oracle_model_eval(const char * model,
   if(m == "centroidal_motion")
     return modelEval<DDPProblemCentroidalMotion, 9, 16>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx,
                                                         Vxx);
+  if(m == "planar_quadrotor")
+    return modelEval<DDPProblemPlanarQuadrotor, 6, 2>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx,
+                                                      Vxx);
   if(m == "fmpc_cartpole")
     return modelEval<FmpcProblemCartPole, 4, 1>(params, t, x, u, x_next, costs, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu, Vx, Vxx);
   if(m == "fmpc_oscillator")

@@ -664,9 +664,20 @@ public:
   {
     for(int i = 0; i < n; i++) b.d[i] = a.d[i];
   }
+  template<class G, class = void>
+  struct HasInputDim : std::false_type
+  {
+  };
+  template<class G>
+  struct HasInputDim<G, std::void_t<decltype(std::declval<const G &>().inputDim(0.0))>> : std::true_type
+  {
+  };
   int inputDim(double t) const override
   {
-    return f_.inputDim(t);
+    if constexpr(HasInputDim<F>::value)
+      return f_.inputDim(t);
+    else
+      return NU;
   }
   StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const override
   {
@@ -742,6 +753,9 @@ using DDPProblemVerticalMotion = DDPProblemFromFunctor<nmpc_b200::models::Vertic
 // centroidal motion, n_x = 9, input dimension 16 or 0 (TestDDPCentroidalMotion.cpp:18-201); pinned by
 // tests/golden/reference_centroidal.npz (the reference's DDPSolver<9, Eigen::Dynamic>, oracle/ref/ref_centroidal.cpp)
 using DDPProblemCentroidalMotion = DDPProblemFromFunctor<nmpc_b200::models::CentroidalMotion<double>>;
+// planar quadrotor, n_x = 6, n_u = 2: the two-input control-limited backward pass (BoxQP<2>, DDPSolver.hpp:450-497);
+// pinned by tests/golden/reference_ddp_planar.npz (the reference's DDPSolver<6, 2>, oracle/ref/ref_ddp.cpp)
+using DDPProblemPlanarQuadrotor = DDPProblemFromFunctor<nmpc_b200::models::PlanarQuadrotor<double>>;
 /** Any host+device FMPC functor F of include/nmpc_b200/models as an oracle problem (ineqDim(t) when F has it). */
 template<class F>
 class FmpcProblemFromFunctor : public FmpcProblem<F::NX, F::NU, F::NG>

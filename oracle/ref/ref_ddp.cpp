@@ -23,6 +23,8 @@
 namespace
 {
 using DDPProblemCartPole = CartPoleBodies<nmpc_ddp::DDPProblem<4, 1>>;
+// two inputs: the control-limited backward pass with BoxQP<2> (DDPSolver.hpp:450-497)
+using DDPProblemPlanarQuadrotor = PlanarQuadrotorBodies<nmpc_ddp::DDPProblem<6, 2>>;
 }
 
 extern "C"
@@ -58,8 +60,14 @@ void ref_ddp_config_default(ref_ddp_config * cfg)
   for(int i = 0; i < cfg->n_alpha; i++) cfg->alpha_list[i] = c.alpha_list[i];
 }
 
-/** One cart-pole DDPSolver::solve() with the reference's code.  Arrays as in oracle_ddp_solve_batch, B = 1. */
-int ref_ddp_solve_cartpole(const double * params,
+} // extern "C"
+
+namespace
+{
+/** One DDPSolver<NX, NU>::solve() with the reference's code.  Arrays as in oracle_ddp_solve_batch, B = 1;
+    u_lo / u_hi [NU] constant limits. */
+template<class Problem, int NX, int NU>
+int refDdpSolve(const double * params,
                            const ref_ddp_config * cfg,
                            double t0,
                            const double * x0,
@@ -73,8 +81,8 @@ int ref_ddp_solve_cartpole(const double * params,
                            int * n_trace_out,
                            int * solve_ret)
 {
-  auto problem = std::make_shared<DDPProblemCartPole>(params);
-  nmpc_ddp::DDPSolver<4, 1> solver(problem);
+  auto problem = std::make_shared<Problem>(params);
+  nmpc_ddp::DDPSolver<NX, NU> solver(problem);
   auto & c = solver.config();
   c.print_level = 0;
   c.with_input_constraint = cfg->with_input_constraint != 0;
@@ -94,19 +102,20 @@ int ref_ddp_solve_cartpole(const double * params,
   c.cost_update_thre = cfg->cost_update_thre;
   if(c.with_input_constraint)
   {
-    const double lo = u_lo[0], hi = u_hi[0];
-    solver.setInputLimitsFunc([lo, hi](double) {
-      std::array<DDPProblemCartPole::InputDimVector, 2> limits;
-      limits[0].setConstant(lo);
-      limits[1].setConstant(hi);
-      return limits;
-    });
+    std::array<typename Problem::InputDimVector, 2> limits;
+    for(int d = 0; d < NU; d++)
+    {
+      limits[0][d] = u_lo[d];
+      limits[1][d] = u_hi[d];
+    }
+    solver.setInputLimitsFunc([limits](double) { return limits; });
   }
   const int N = cfg->horizon_steps;
-  DDPProblemCartPole::StateDimVector current_x;
-  current_x << x0[0], x0[1], x0[2], x0[3];
-  std::vector<DDPProblemCartPole::InputDimVector> initial_u_list(N);
-  for(int i = 0; i < N; i++) initial_u_list[i][0] = u_init[i];
+  typename Problem::StateDimVector current_x;
+  for(int d = 0; d < NX; d++) current_x[d] = x0[d];
+  std::vector<typename Problem::InputDimVector> initial_u_list(N);
+  for(int i = 0; i < N; i++)
+    for(int d = 0; d < NU; d++) initial_u_list[i][d] = u_init[i * NU + d];
   // the unconstrained branch prints "[DDP/Forward] Value is not expected to decrease." even at print_level 0
   std::streambuf * old = std::cout.rdbuf(nullptr);
   bool ret = false;
@@ -124,10 +133,11 @@ int ref_ddp_solve_cartpole(const double * params,
   const auto & cd = solver.controlData();
   for(int i = 0; i <= N; i++)
   {
-    for(int d = 0; d < 4; d++) x_out[i * 4 + d] = cd.x_list[i][d];
+    for(int d = 0; d < NX; d++) x_out[i * NX + d] = cd.x_list[i][d];
     cost_out[i] = cd.cost_list[i];
   }
-  for(int i = 0; i < N; i++) u_out[i] = cd.u_list[i][0];
+  for(int i = 0; i < N; i++)
+    for(int d = 0; d < NU; d++) u_out[i * NU + d] = cd.u_list[i][d];
   const auto & tl = solver.traceDataList();
   std::memset(trace_out, 0, sizeof(double) * (cfg->max_iter + 1) * 9);
   for(size_t r = 0; r < tl.size(); r++)
@@ -139,6 +149,46 @@ int ref_ddp_solve_cartpole(const double * params,
   }
   *n_trace_out = (int)tl.size();
   return 0;
+}
+} // namespace
+
+extern "C"
+{
+int ref_ddp_solve_cartpole(const double * params,
+                           const ref_ddp_config * cfg,
+                           double t0,
+                           const double * x0,
+                           const double * u_init,
+                           const double * u_lo,
+                           const double * u_hi,
+                           double * x_out,
+                           double * u_out,
+                           double * cost_out,
+                           double * trace_out,
+                           int * n_trace_out,
+                           int * solve_ret)
+{
+  return refDdpSolve<DDPProblemCartPole, 4, 1>(params, cfg, t0, x0, u_init, u_lo, u_hi, x_out, u_out, cost_out, trace_out,
+                                               n_trace_out, solve_ret);
+}
+
+/** The planar quadrotor (n_x = 6, n_u = 2) through the reference's DDPSolver<6, 2>, with BoxQP<2> when limits are on. */
+int ref_ddp_solve_planar(const double * params,
+                         const ref_ddp_config * cfg,
+                         double t0,
+                         const double * x0,
+                         const double * u_init,
+                         const double * u_lo,
+                         const double * u_hi,
+                         double * x_out,
+                         double * u_out,
+                         double * cost_out,
+                         double * trace_out,
+                         int * n_trace_out,
+                         int * solve_ret)
+{
+  return refDdpSolve<DDPProblemPlanarQuadrotor, 6, 2>(params, cfg, t0, x0, u_init, u_lo, u_hi, x_out, u_out, cost_out,
+                                                      trace_out, n_trace_out, solve_ret);
 }
 
 /** A batch of cart-pole solves with the reference's code: one DDPSolver object per OpenMP thread, instances

@@ -157,135 +157,17 @@ public:
   }
 };
 
-/** The planar quadrotor of include/nmpc_b200/models/planar_quadrotor.h (two inputs, four thrust limits) written as a
-    user of the reference would: an nmpc_fmpc::FmpcProblem<6, 2, 4> in Eigen idiom.  Not one of the reference's tests --
-    it exists to drive the n_u > 1 branch of FmpcSolver::backwardPass (LDLT / FullPivLU of G, FmpcSolver.hpp:596-617).
-    params: [dt, mass, inertia, arm, thrust_max, running_x[6], running_u, running_u_cross, terminal_x[6], ref_px, ref_pz]. */
-class FmpcProblemPlanarQuadrotor : public nmpc_fmpc::FmpcProblem<6, 2, 4>
+/** ... as an FMPC problem: 0 <= T_a <= thrust_max. */
+class FmpcProblemPlanarQuadrotor : public PlanarQuadrotorBodies<nmpc_fmpc::FmpcProblem<6, 2, 4>>
 {
 public:
   static constexpr bool kDynamicIneq = false;
-  explicit FmpcProblemPlanarQuadrotor(const double * p) : FmpcProblem(p[0])
-  {
-    mass_ = p[1];
-    inertia_ = p[2];
-    arm_ = p[3];
-    thrust_max_ = p[4];
-    for(int i = 0; i < 6; i++) running_x_[i] = p[5 + i];
-    running_u_ = p[11];
-    running_u_cross_ = p[12];
-    for(int i = 0; i < 6; i++) terminal_x_[i] = p[13 + i];
-    ref_.setZero();
-    ref_[0] = p[19];
-    ref_[1] = p[20];
-  }
-  double hover() const
-  {
-    return 0.5 * mass_ * 9.80665;
-  }
-  StateDimVector stateEq(double, const StateDimVector & x, const InputDimVector & u) const override
-  {
-    const double st = std::sin(x[2]), ct = std::cos(x[2]);
-    const double thrust = u[0] + u[1];
-    StateDimVector x_dot;
-    x_dot << x[3], x[4], x[5], -1 * thrust * st / mass_, thrust * ct / mass_ - 9.80665, arm_ * (u[0] - u[1]) / inertia_;
-    return x + dt_ * x_dot;
-  }
-  double runningCost(double, const StateDimVector & x, const InputDimVector & u) const override
-  {
-    double sx = 0;
-    for(int i = 0; i < 6; i++)
-    {
-      const double e = x[i] - ref_[i];
-      sx += running_x_[i] * (e * e);
-    }
-    const double e0 = u[0] - hover(), e1 = u[1] - hover();
-    const double su = running_u_ * (e0 * e0 + e1 * e1);
-    return (0.5 * sx + 0.5 * su) + running_u_cross_ * (e0 * e1);
-  }
-  double terminalCost(double, const StateDimVector & x) const override
-  {
-    double sx = 0;
-    for(int i = 0; i < 6; i++)
-    {
-      const double e = x[i] - ref_[i];
-      sx += terminal_x_[i] * (e * e);
-    }
-    return 0.5 * sx;
-  }
+  using PlanarQuadrotorBodies<nmpc_fmpc::FmpcProblem<6, 2, 4>>::PlanarQuadrotorBodies;
   IneqDimVector ineqConst(double, const StateDimVector &, const InputDimVector & u) const override
   {
     IneqDimVector g;
     g << -1 * u[0], u[0] - thrust_max_, -1 * u[1], u[1] - thrust_max_;
     return g;
-  }
-  void calcStateEqDeriv(double,
-                        const StateDimVector & x,
-                        const InputDimVector & u,
-                        Eigen::Ref<StateStateDimMatrix> state_eq_deriv_x,
-                        Eigen::Ref<StateInputDimMatrix> state_eq_deriv_u) const override
-  {
-    const double st = std::sin(x[2]), ct = std::cos(x[2]);
-    const double thrust = u[0] + u[1];
-    state_eq_deriv_x.setZero();
-    state_eq_deriv_x(0, 3) = 1;
-    state_eq_deriv_x(1, 4) = 1;
-    state_eq_deriv_x(2, 5) = 1;
-    state_eq_deriv_x(3, 2) = -1 * thrust * ct / mass_;
-    state_eq_deriv_x(4, 2) = -1 * thrust * st / mass_;
-    state_eq_deriv_x *= dt_;
-    state_eq_deriv_x.diagonal().array() += 1;
-    state_eq_deriv_u.setZero();
-    state_eq_deriv_u(3, 0) = -1 * st / mass_;
-    state_eq_deriv_u(3, 1) = -1 * st / mass_;
-    state_eq_deriv_u(4, 0) = ct / mass_;
-    state_eq_deriv_u(4, 1) = ct / mass_;
-    state_eq_deriv_u(5, 0) = arm_ / inertia_;
-    state_eq_deriv_u(5, 1) = -1 * arm_ / inertia_;
-    state_eq_deriv_u *= dt_;
-  }
-  void calcRunningCostDeriv(double,
-                            const StateDimVector & x,
-                            const InputDimVector & u,
-                            Eigen::Ref<StateDimVector> running_cost_deriv_x,
-                            Eigen::Ref<InputDimVector> running_cost_deriv_u) const override
-  {
-    for(int i = 0; i < 6; i++) running_cost_deriv_x[i] = running_x_[i] * (x[i] - ref_[i]);
-    const double e0 = u[0] - hover(), e1 = u[1] - hover();
-    running_cost_deriv_u[0] = running_u_ * e0 + running_u_cross_ * e1;
-    running_cost_deriv_u[1] = running_u_ * e1 + running_u_cross_ * e0;
-  }
-  void calcRunningCostDeriv(double t,
-                            const StateDimVector & x,
-                            const InputDimVector & u,
-                            Eigen::Ref<StateDimVector> running_cost_deriv_x,
-                            Eigen::Ref<InputDimVector> running_cost_deriv_u,
-                            Eigen::Ref<StateStateDimMatrix> running_cost_deriv_xx,
-                            Eigen::Ref<InputInputDimMatrix> running_cost_deriv_uu,
-                            Eigen::Ref<StateInputDimMatrix> running_cost_deriv_xu) const override
-  {
-    calcRunningCostDeriv(t, x, u, running_cost_deriv_x, running_cost_deriv_u);
-    running_cost_deriv_xx.setZero();
-    for(int i = 0; i < 6; i++) running_cost_deriv_xx(i, i) = running_x_[i];
-    running_cost_deriv_uu(0, 0) = running_u_;
-    running_cost_deriv_uu(1, 1) = running_u_;
-    running_cost_deriv_uu(0, 1) = running_u_cross_;
-    running_cost_deriv_uu(1, 0) = running_u_cross_;
-    running_cost_deriv_xu.setZero();
-  }
-  void calcTerminalCostDeriv(double, const StateDimVector & x, Eigen::Ref<StateDimVector> terminal_cost_deriv_x)
-      const override
-  {
-    for(int i = 0; i < 6; i++) terminal_cost_deriv_x[i] = terminal_x_[i] * (x[i] - ref_[i]);
-  }
-  void calcTerminalCostDeriv(double t,
-                             const StateDimVector & x,
-                             Eigen::Ref<StateDimVector> terminal_cost_deriv_x,
-                             Eigen::Ref<StateStateDimMatrix> terminal_cost_deriv_xx) const override
-  {
-    calcTerminalCostDeriv(t, x, terminal_cost_deriv_x);
-    terminal_cost_deriv_xx.setZero();
-    for(int i = 0; i < 6; i++) terminal_cost_deriv_xx(i, i) = terminal_x_[i];
   }
   void calcIneqConstDeriv(double,
                           const StateDimVector &,
@@ -301,9 +183,6 @@ public:
     ineq_const_deriv_u(3, 1) = 1;
   }
 
-protected:
-  double mass_, inertia_, arm_, thrust_max_, running_x_[6], running_u_, running_u_cross_, terminal_x_[6];
-  StateDimVector ref_;
 };
 
 /** Cart-pole whose position limits exist only for window_start <= t < window_end: the reference's DYNAMIC inequality
