@@ -207,6 +207,64 @@ extern "C"
       same path twice is harmless.  NMPC_B200_ERR_RUNTIME with the loader's message when the library cannot be loaded. */
   int nmpc_b200_load_plugin(const char * path);
 
+  /* ------------------------------------------------------------- several GPUs, one box ---- */
+
+  /** A batch of DDPSolver objects SHARDED over several GPUs of one box from ONE process: a solver handle, a stream and
+      a host worker thread per device.  Instances never interact (the reference runs one DDPSolver object per problem,
+      DDPSolver.h:329-374), so instance b of a solve with B instances lives on shard s with
+      begin(s) <= b < end(s), begin(s) = s * (B / n) + min(s, B % n): contiguous chunks, sizes differing by at most one,
+      and no collective on the data path.  `devices` = CUDA ordinals (NULL: 0 .. n_devices-1; n_devices <= 0: every
+      visible device; an ordinal may appear more than once: two shards then share that device, each with
+      its own stream).  `total_capacity` = the largest B of any later solve. */
+  typedef struct nmpc_b200_ddp_sharded nmpc_b200_ddp_sharded;
+  int nmpc_b200_ddp_create_sharded(const char * model,
+                                   const double * params,
+                                   int n_params,
+                                   const nmpc_b200_ddp_config * cfg,
+                                   int total_capacity,
+                                   const int * devices,
+                                   int n_devices,
+                                   nmpc_b200_ddp_sharded ** out);
+  int nmpc_b200_ddp_sharded_destroy(nmpc_b200_ddp_sharded * h);
+  int nmpc_b200_ddp_sharded_num_shards(const nmpc_b200_ddp_sharded * h);
+  /** The single-GPU handle behind shard `shard` (owned by the sharded handle), e.g. for the timing entries. */
+  nmpc_b200_ddp * nmpc_b200_ddp_sharded_shard(nmpc_b200_ddp_sharded * h, int shard);
+  /** [begin, end) of shard `shard` for a solve with B instances; *device = its CUDA ordinal (any may be NULL). */
+  int nmpc_b200_ddp_sharded_range(const nmpc_b200_ddp_sharded * h, int B, int shard, int * begin, int * end, int * device);
+  /** DDPSolver::config() / setInputLimitsFunc for every shard. */
+  int nmpc_b200_ddp_sharded_set_config(nmpc_b200_ddp_sharded * h, const nmpc_b200_ddp_config * cfg);
+  int nmpc_b200_ddp_sharded_set_input_limits(nmpc_b200_ddp_sharded * h, const double * lower, const double * upper);
+  /** DDPSolver::solve for B <= total_capacity instances from HOST arrays x0[B][NX], u_init[B][N][NU]: every shard copies
+      its chunk in and solves on its own device, all shards at once; returns when all have finished. */
+  int nmpc_b200_ddp_sharded_solve(nmpc_b200_ddp_sharded * h,
+                                  int B,
+                                  double current_t,
+                                  const double * x0,
+                                  const double * u_init,
+                                  int n_u_steps);
+  /** nmpc_b200_ddp_get over all shards: field `what` of the last solve, [B][...] in instance order.  dst_device < 0:
+      dst is host memory.  dst_device >= 0: dst is memory of that CUDA device and every shard's gather kernel stores its
+      rows straight into it (over NVLink for the shards on other devices; peer access is enabled on first use). */
+  int nmpc_b200_ddp_sharded_get(nmpc_b200_ddp_sharded * h, int what, void * dst, size_t dst_bytes, int dst_device);
+
+  /** Several PROCESSES (one per GPU, e.g. under torchrun / MPI): a device buffer every process of the box can store
+      into.  The owner creates it (cudaMalloc, zero-filled) and hands the 64-byte handle to the other processes by any
+      host channel; they open it and pass `ptr + offset` as a device destination to nmpc_b200_ddp_get /
+      nmpc_b200_fmpc_get, whose gather kernel then writes its rows directly into the owner's memory -- the first-step
+      controls of all shards land in one place without a collective.  peer_signal / peer_wait order it: after its
+      stores a process signals flag[rank] <- value (release, system scope) on its stream; the owner's stream waits until
+      n flags have reached `value`.  peer_wait gives up after timeout_ms (NMPC_B200_ERR_RUNTIME at the next
+      nmpc_b200_peer_check) instead of hanging the device. */
+  int nmpc_b200_peer_buffer_create(size_t bytes, int device, void ** ptr, unsigned char handle[64]);
+  int nmpc_b200_peer_buffer_open(const unsigned char handle[64], int device, void ** ptr);
+  int nmpc_b200_peer_buffer_close(void * ptr, int device);
+  int nmpc_b200_peer_buffer_destroy(void * ptr, int device);
+  int nmpc_b200_peer_signal(void * flag, unsigned long long value, int device, void * stream);
+  int nmpc_b200_peer_wait(void * flags, int n_flags, unsigned long long value, int timeout_ms, int device, void * stream);
+  /** Synchronises `stream` and reports whether a peer_wait on flags timed out since the last check (flags[n_flags] is
+      the time-out word, so the buffer needs n_flags + 1 words). */
+  int nmpc_b200_peer_check(void * flags, int n_flags, int device, void * stream);
+
   /* ------------------------------------------------------- receding-horizon (MPC) loop ---- */
 
   /** The MPC loops that call the solvers in the reference (TestDDPBipedal.cpp:243-268,

@@ -20,6 +20,146 @@
 
 #include "ref_models.h"
 
+#include <nmpc_b200/models/quadrotor.h>
+
+namespace
+{
+/** A functor of include/nmpc_b200/models (the same source the CUDA kernels and oracle/ evaluate) behind the REFERENCE's
+    DDPProblem interface, so that the reference's DDPSolver runs on models that none of its own tests define. */
+template<class F>
+class RefProblemFromFunctor : public nmpc_ddp::DDPProblem<F::NX, F::NU>
+{
+public:
+  using Base = nmpc_ddp::DDPProblem<F::NX, F::NU>;
+  using StateDimVector = typename Base::StateDimVector;
+  using InputDimVector = typename Base::InputDimVector;
+  using StateStateDimMatrix = typename Base::StateStateDimMatrix;
+  using InputInputDimMatrix = typename Base::InputInputDimMatrix;
+  using StateInputDimMatrix = typename Base::StateInputDimMatrix;
+  static constexpr int NX = F::NX, NU = F::NU;
+
+  explicit RefProblemFromFunctor(const double * p) : Base(p[0]), f_(F::fromParams(p)) {}
+
+  static typename F::StateDimVector fx(const StateDimVector & x)
+  {
+    typename F::StateDimVector v;
+    for(int i = 0; i < NX; i++) v[i] = x[i];
+    return v;
+  }
+  static typename F::InputDimVector fu(const InputDimVector & u)
+  {
+    typename F::InputDimVector v;
+    for(int i = 0; i < NU; i++) v[i] = u[i];
+    return v;
+  }
+  StateDimVector stateEq(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    const typename F::StateDimVector n = f_.stateEq(t, fx(x), fu(u));
+    StateDimVector out;
+    for(int i = 0; i < NX; i++) out[i] = n[i];
+    return out;
+  }
+  double runningCost(double t, const StateDimVector & x, const InputDimVector & u) const override
+  {
+    return f_.runningCost(t, fx(x), fu(u));
+  }
+  double terminalCost(double t, const StateDimVector & x) const override
+  {
+    return f_.terminalCost(t, fx(x));
+  }
+  void calcStateEqDeriv(double t,
+                        const StateDimVector & x,
+                        const InputDimVector & u,
+                        Eigen::Ref<StateStateDimMatrix> state_eq_deriv_x,
+                        Eigen::Ref<StateInputDimMatrix> state_eq_deriv_u) const override
+  {
+    typename F::StateStateDimMatrix a;
+    typename F::StateInputDimMatrix b;
+    f_.calcStateEqDeriv(t, fx(x), fu(u), a, b);
+    for(int j = 0; j < NX; j++)
+      for(int i = 0; i < NX; i++) state_eq_deriv_x(i, j) = a(i, j);
+    for(int j = 0; j < NU; j++)
+      for(int i = 0; i < NX; i++) state_eq_deriv_u(i, j) = b(i, j);
+  }
+  void calcStateEqDeriv(double,
+                        const StateDimVector &,
+                        const InputDimVector &,
+                        Eigen::Ref<StateStateDimMatrix>,
+                        Eigen::Ref<StateInputDimMatrix>,
+                        std::vector<StateStateDimMatrix> &,
+                        std::vector<InputInputDimMatrix> &,
+                        std::vector<StateInputDimMatrix> &) const override
+  {
+    throw std::runtime_error("Second-order derivatives of state equation are not implemented.");
+  }
+  void calcRunningCostDeriv(double t,
+                            const StateDimVector & x,
+                            const InputDimVector & u,
+                            Eigen::Ref<StateDimVector> running_cost_deriv_x,
+                            Eigen::Ref<InputDimVector> running_cost_deriv_u) const override
+  {
+    // the functors have the second-order overload only
+    typename F::StateDimVector lx;
+    typename F::InputDimVector lu;
+    typename F::StateStateDimMatrix lxx;
+    typename F::InputInputDimMatrix luu;
+    typename F::StateInputDimMatrix lxu;
+    f_.calcRunningCostDeriv(t, fx(x), fu(u), lx, lu, lxx, luu, lxu);
+    for(int i = 0; i < NX; i++) running_cost_deriv_x[i] = lx[i];
+    for(int i = 0; i < NU; i++) running_cost_deriv_u[i] = lu[i];
+  }
+  void calcRunningCostDeriv(double t,
+                            const StateDimVector & x,
+                            const InputDimVector & u,
+                            Eigen::Ref<StateDimVector> running_cost_deriv_x,
+                            Eigen::Ref<InputDimVector> running_cost_deriv_u,
+                            Eigen::Ref<StateStateDimMatrix> running_cost_deriv_xx,
+                            Eigen::Ref<InputInputDimMatrix> running_cost_deriv_uu,
+                            Eigen::Ref<StateInputDimMatrix> running_cost_deriv_xu) const override
+  {
+    typename F::StateDimVector lx;
+    typename F::InputDimVector lu;
+    typename F::StateStateDimMatrix lxx;
+    typename F::InputInputDimMatrix luu;
+    typename F::StateInputDimMatrix lxu;
+    f_.calcRunningCostDeriv(t, fx(x), fu(u), lx, lu, lxx, luu, lxu);
+    for(int i = 0; i < NX; i++) running_cost_deriv_x[i] = lx[i];
+    for(int i = 0; i < NU; i++) running_cost_deriv_u[i] = lu[i];
+    for(int j = 0; j < NX; j++)
+      for(int i = 0; i < NX; i++) running_cost_deriv_xx(i, j) = lxx(i, j);
+    for(int j = 0; j < NU; j++)
+      for(int i = 0; i < NU; i++) running_cost_deriv_uu(i, j) = luu(i, j);
+    for(int j = 0; j < NU; j++)
+      for(int i = 0; i < NX; i++) running_cost_deriv_xu(i, j) = lxu(i, j);
+  }
+  void calcTerminalCostDeriv(double t, const StateDimVector & x, Eigen::Ref<StateDimVector> terminal_cost_deriv_x)
+      const override
+  {
+    typename F::StateDimVector vx;
+    typename F::StateStateDimMatrix vxx;
+    f_.calcTerminalCostDeriv(t, fx(x), vx, vxx);
+    for(int i = 0; i < NX; i++) terminal_cost_deriv_x[i] = vx[i];
+  }
+  void calcTerminalCostDeriv(double t,
+                             const StateDimVector & x,
+                             Eigen::Ref<StateDimVector> terminal_cost_deriv_x,
+                             Eigen::Ref<StateStateDimMatrix> terminal_cost_deriv_xx) const override
+  {
+    typename F::StateDimVector vx;
+    typename F::StateStateDimMatrix vxx;
+    f_.calcTerminalCostDeriv(t, fx(x), vx, vxx);
+    for(int i = 0; i < NX; i++) terminal_cost_deriv_x[i] = vx[i];
+    for(int j = 0; j < NX; j++)
+      for(int i = 0; i < NX; i++) terminal_cost_deriv_xx(i, j) = vxx(i, j);
+  }
+
+protected:
+  F f_;
+};
+// four inputs, twelve states: BoxQP<4> with several free / clamped inputs per step
+using DDPProblemQuadrotor = RefProblemFromFunctor<nmpc_b200::models::Quadrotor<double>>;
+} // namespace
+
 namespace
 {
 using DDPProblemCartPole = CartPoleBodies<nmpc_ddp::DDPProblem<4, 1>>;
@@ -170,6 +310,25 @@ int ref_ddp_solve_cartpole(const double * params,
 {
   return refDdpSolve<DDPProblemCartPole, 4, 1>(params, cfg, t0, x0, u_init, u_lo, u_hi, x_out, u_out, cost_out, trace_out,
                                                n_trace_out, solve_ret);
+}
+
+/** The 3-D quadrotor functor (n_x = 12, n_u = 4) through the reference's DDPSolver<12, 4>, with BoxQP<4>. */
+int ref_ddp_solve_quadrotor(const double * params,
+                            const ref_ddp_config * cfg,
+                            double t0,
+                            const double * x0,
+                            const double * u_init,
+                            const double * u_lo,
+                            const double * u_hi,
+                            double * x_out,
+                            double * u_out,
+                            double * cost_out,
+                            double * trace_out,
+                            int * n_trace_out,
+                            int * solve_ret)
+{
+  return refDdpSolve<DDPProblemQuadrotor, 12, 4>(params, cfg, t0, x0, u_init, u_lo, u_hi, x_out, u_out, cost_out,
+                                                 trace_out, n_trace_out, solve_ret);
 }
 
 /** The planar quadrotor (n_x = 6, n_u = 2) through the reference's DDPSolver<6, 2>, with BoxQP<2> when limits are on. */

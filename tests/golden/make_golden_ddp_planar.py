@@ -73,6 +73,14 @@ def main():
     # zero initial inputs (outside the box): the first forward pass starts from an infeasible input sequence
     case("planar_box_cold", p, x0s, N, lo=[0.7 * hover, 0.7 * hover], hi=[1.4 * hover, 1.4 * hover],
          with_input_constraint=1, max_iter=80)
+    # The two cases above are ones where the REFERENCE itself is discontinuous in the last bit of its input from the
+    # third iteration on (tests/test_ddp_planar.py::test_reference_splits_on_the_last_bit_at_a_limit); their first two
+    # iterations are not, and are what an implementation with different rounding can be held to exactly.
+    case("planar_box_cross_fixed_it2", q, x0s, N, lo=[0.85 * hover, 0.85 * hover], hi=[1.3 * hover, 1.1 * hover],
+         u_init=uh, with_input_constraint=1, max_iter=2, k_rel_norm_thre=0.0, cost_update_thre=0.0,
+         cost_update_ratio_thre=0.0, lambda_thre=0.0, reg_type=2)
+    case("planar_box_cold_it2", p, x0s, N, lo=[0.7 * hover, 0.7 * hover], hi=[1.4 * hover, 1.4 * hover],
+         with_input_constraint=1, max_iter=2)
     out = os.path.join(HERE, "reference_ddp_planar.npz")
     np.savez_compressed(out, **CASES)
     print("wrote", out, os.path.getsize(out), "bytes")

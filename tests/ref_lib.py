@@ -68,20 +68,30 @@ def ddp_solve_cartpole(params, cfg, x0, u_init, t0=0.0, u_lo=None, u_hi=None):
 
 def ddp_solve_planar(params, cfg, x0, u_init, t0=0.0, u_lo=None, u_hi=None):
     """The reference's DDPSolver<6, 2> on the planar quadrotor (oracle/ref/ref_models.h); BoxQP<2> when limits are on."""
+    return _ddp_solve_nxnu("ref_ddp_solve_planar", 6, 2, params, cfg, x0, u_init, t0, u_lo, u_hi)
+
+
+def ddp_solve_quadrotor(params, cfg, x0, u_init, t0=0.0, u_lo=None, u_hi=None):
+    """The reference's DDPSolver<12, 4> on the 3-D quadrotor functor (include/nmpc_b200/models/quadrotor.h behind the
+    reference's DDPProblem interface); BoxQP<4> when limits are on."""
+    return _ddp_solve_nxnu("ref_ddp_solve_quadrotor", 12, 4, params, cfg, x0, u_init, t0, u_lo, u_hi)
+
+
+def _ddp_solve_nxnu(entry, nx, nu, params, cfg, x0, u_init, t0, u_lo, u_hi):
     N = cfg.horizon_steps
-    x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(6)
-    u_init = np.ascontiguousarray(u_init, dtype=np.float64).reshape(N, 2)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(nx)
+    u_init = np.ascontiguousarray(u_init, dtype=np.float64).reshape(N, nu)
     params = np.ascontiguousarray(params, dtype=np.float64)
-    out = {"x": np.zeros((N + 1, 6)), "u": np.zeros((N, 2)), "cost_list": np.zeros(N + 1),
+    out = {"x": np.zeros((N + 1, nx)), "u": np.zeros((N, nu)), "cost_list": np.zeros(N + 1),
            "trace": np.zeros((cfg.max_iter + 1, 9))}
     n_trace, ret = C.c_int(), C.c_int()
-    lo = None if u_lo is None else np.ascontiguousarray(u_lo, dtype=np.float64).reshape(2)
-    hi = None if u_hi is None else np.ascontiguousarray(u_hi, dtype=np.float64).reshape(2)
-    rc = lib().ref_ddp_solve_planar(_p(params), C.byref(cfg), C.c_double(t0), _p(x0), _p(u_init), _p(lo), _p(hi),
+    lo = None if u_lo is None else np.ascontiguousarray(u_lo, dtype=np.float64).reshape(nu)
+    hi = None if u_hi is None else np.ascontiguousarray(u_hi, dtype=np.float64).reshape(nu)
+    rc = getattr(lib(), entry)(_p(params), C.byref(cfg), C.c_double(t0), _p(x0), _p(u_init), _p(lo), _p(hi),
                                     _p(out["x"]), _p(out["u"]), _p(out["cost_list"]), _p(out["trace"]),
                                     C.byref(n_trace), C.byref(ret))
     if rc != 0:
-        raise RuntimeError("reference DDPSolver<6, 2>::solve threw")
+        raise RuntimeError("reference DDPSolver::solve threw")
     out["n_trace"], out["solve_ret"] = n_trace.value, ret.value
     return out
 
