@@ -93,6 +93,11 @@ EXPORTED_SYMBOLS = [
     "nmpc_b200_fmpc_config_default", "nmpc_b200_fmpc_create", "nmpc_b200_fmpc_destroy", "nmpc_b200_fmpc_set_config",
     "nmpc_b200_fmpc_solve", "nmpc_b200_fmpc_get", "nmpc_b200_fmpc_sync", "nmpc_b200_fmpc_enable_timing",
     "nmpc_b200_fmpc_get_durations", "nmpc_b200_fmpc_run_mpc",
+    "nmpc_b200_ddp_create_sharded", "nmpc_b200_ddp_sharded_destroy", "nmpc_b200_ddp_sharded_num_shards",
+    "nmpc_b200_ddp_sharded_shard", "nmpc_b200_ddp_sharded_range", "nmpc_b200_ddp_sharded_set_config",
+    "nmpc_b200_ddp_sharded_set_input_limits", "nmpc_b200_ddp_sharded_solve", "nmpc_b200_ddp_sharded_get",
+    "nmpc_b200_peer_buffer_create", "nmpc_b200_peer_buffer_open", "nmpc_b200_peer_buffer_close",
+    "nmpc_b200_peer_buffer_destroy", "nmpc_b200_peer_signal", "nmpc_b200_peer_wait", "nmpc_b200_peer_check",
 ]
 
 _lib = None
@@ -132,6 +137,24 @@ def lib():
         L.nmpc_b200_load_plugin.argtypes = [C.c_char_p]
         L.nmpc_b200_ddp_set_input_limits_mpc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.nmpc_b200_ddp_get_iteration_durations.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.nmpc_b200_ddp_create_sharded.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                   C.c_int, C.c_void_p]
+        L.nmpc_b200_ddp_sharded_destroy.argtypes = [C.c_void_p]
+        L.nmpc_b200_ddp_sharded_num_shards.argtypes = [C.c_void_p]
+        L.nmpc_b200_ddp_sharded_shard.argtypes = [C.c_void_p, C.c_int]
+        L.nmpc_b200_ddp_sharded_shard.restype = C.c_void_p
+        L.nmpc_b200_ddp_sharded_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nmpc_b200_ddp_sharded_set_config.argtypes = [C.c_void_p, C.c_void_p]
+        L.nmpc_b200_ddp_sharded_set_input_limits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nmpc_b200_ddp_sharded_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        L.nmpc_b200_ddp_sharded_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+        L.nmpc_b200_peer_buffer_create.argtypes = [C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+        L.nmpc_b200_peer_buffer_open.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.nmpc_b200_peer_buffer_close.argtypes = [C.c_void_p, C.c_int]
+        L.nmpc_b200_peer_buffer_destroy.argtypes = [C.c_void_p, C.c_int]
+        L.nmpc_b200_peer_signal.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p]
+        L.nmpc_b200_peer_wait.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_int, C.c_int, C.c_void_p]
+        L.nmpc_b200_peer_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.nmpc_b200_fmpc_solve.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 6 + [C.c_int, C.c_int,
                                                                                                   C.c_void_p]
         L.nmpc_b200_fmpc_run_mpc.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 6 + [C.c_int] + [

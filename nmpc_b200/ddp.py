@@ -330,6 +330,11 @@ class DDPSolver:
         """Copy field `what` into a preallocated numpy array or float64 torch CUDA tensor."""
         return self._get_f64(what, tuple(out.shape), out=out, stream=stream)
 
+    def get_to_device_ptr(self, what, ptr, nbytes, stream=None):
+        """Field `what` into device memory given as a raw address -- e.g. a row of a sharding.PeerBuffer that lives on
+        another GPU / in another process: the gather kernel stores straight into it."""
+        check(lib().nmpc_b200_ddp_get(self._h, int(what), C.c_void_p(int(ptr)), int(nbytes), 1, self._stream_ptr(stream)))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             lib().nmpc_b200_ddp_destroy(self._h)
