@@ -408,7 +408,11 @@ def main():
     ap.add_argument("--total-batch", type=int, default=None, help="instances in total, split over the ranks (strong scaling)")
     ap.add_argument("--mode", default="fixed", choices=["fixed", "ref"])
     ap.add_argument("--seed", type=int, default=None)
-    ap.add_argument("--no-gather", action="store_true", help="skip the NCCL all-gather of first-step controls (N>1)")
+    ap.add_argument("--no-gather", action="store_true", help="skip the gather of first-step controls (N>1)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how the first-step controls of all shards reach rank 0 -- 'peer': every rank's gather kernel "
+                         "stores its rows into rank 0's buffer over NVLink and raises a flag (no collective); 'nccl': "
+                         "all_gather_into_tensor")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-sample", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -466,6 +470,13 @@ def main():
     gathered = torch.empty((world * B, NU), dtype=torch.float64, device=dev) if world > 1 else None
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     do_gather = world > 1 and not args.no_gather
+    use_peer = do_gather and args.gather == "peer" and not is_fmpc
+    peer, peer_step = None, [0]
+    if use_peer:
+        from nmpc_b200.ddp import F_U0
+        from nmpc_b200.sharding import PeerBuffer
+
+        peer = PeerBuffer(world * B, NU * 8, local_rank, owner=0)
     var_np = wl.fmpc_variable(B) if is_fmpc else None
 
     def make_var(to_torch):
@@ -488,6 +499,14 @@ def main():
                 u0_out.copy_(torch.from_numpy(solver.u0()))
         else:
             solver.solve_batch(0.0, x0_d, u_init_d, stream=stream, read_status=False)
+            if use_peer:
+                # this shard's u_list[0] rows go straight into rank 0's buffer; rank 0's stream waits for all flags
+                peer_step[0] += 1
+                solver.get_to_device_ptr(F_U0, peer.row_ptr(rank * B), B * NU * 8, stream=stream)
+                peer.signal(peer_step[0], stream.cuda_stream)
+                if rank == 0:
+                    peer.wait(peer_step[0], stream.cuda_stream)
+                return
             solver.u0(out=u0_out, stream=stream)
         if do_gather:
             dist.all_gather_into_tensor(gathered, u0_out)
@@ -518,6 +537,8 @@ def main():
     if rank == 0:
         sampler.start()
     total_ms, _ = timed_loop(device_step, args.steps)
+    if use_peer and rank == 0:
+        peer.check(stream.cuda_stream)  # raises if a rank's flag never arrived
 
     # ---- per-kernel durations for the roofline (CUDA events inside the engine, same stream) ----
     solver.enable_timing(True)
@@ -597,7 +618,8 @@ def main():
             work = {"iterations_mean": float(solver.iterations().mean()),
                     "forward_passes_mean": float(solver.n_forward().mean()),
                     "backward_passes_mean": float(solver.n_backward().mean())}
-        work["nccl_collectives_per_step"] = 1 if do_gather else 0
+        work["nccl_collectives_per_step"] = 1 if (do_gather and not use_peer) else 0
+        work["gather_u0"] = ("peer stores + flags" if use_peer else "nccl all_gather") if do_gather else "none"
 
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -625,6 +647,8 @@ def main():
 
     if world > 1:
         dist.barrier()
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 

@@ -216,7 +216,8 @@ __device__ __forceinline__ void produceSweepLanes(const M & model_in_constant_ba
   constexpr int NX = M::NX, NU = M::NU;
   using T = LaneTile<NX, NU>;
   using V = typename Vec2<S>::type;
-  const M model = model_in_constant_bank;
+  using LM = typename LatencyOf<M>::type;
+  const LM model(model_in_constant_bank);
   const S t0 = prm.t0;
   const size_t Bp = ws.Bp;
   const int N = prm.N;
@@ -251,7 +252,7 @@ __device__ __forceinline__ void produceSweepLanes(const M & model_in_constant_ba
     Matrix<S, NX, 1> Lx;
     Matrix<S, NU, 1> Lu;
     Matrix<S, NU, NU> Luu;
-    linearizeStep<M>(model, t0 + i * model.dt(), x, u, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu);
+    linearizeStep<LM>(model, t0 + i * model.dt(), x, u, Fx, Fu, Lx, Lu, Lxx, Luu, Lxu);
 
     S v[T::SIZE];
 #pragma unroll
@@ -826,12 +827,13 @@ __device__ __forceinline__ void laneBackward(const M & model_in_constant_bank,
     }
     else
     {
-      const M model = model_in_constant_bank;
+      using LM = typename LatencyOf<M>::type;
+      const LM model(model_in_constant_bank);
       if(need) n_bwd++;
       const bool ok = (prm.reg_type == 2)
-                          ? laneSweep<M, CONSTRAINED, true, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1, x2, sm.full,
+                          ? laneSweep<LM, CONSTRAINED, true, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1, x2, sm.full,
                                                                  sm.empty, fill, need, lambda, dV0, dV1, k_rel_norm)
-                          : laneSweep<M, CONSTRAINED, false, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1, x2, sm.full,
+                          : laneSweep<LM, CONSTRAINED, false, XCH>(model, ws, prm, b, t, lane, j, jj, xs, sm.ring, x1, x2, sm.full,
                                                                   sm.empty, fill, need, lambda, dV0, dV1, k_rel_norm);
       if(need)
       {

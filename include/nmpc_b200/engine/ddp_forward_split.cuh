@@ -359,19 +359,20 @@ __global__ void __launch_bounds__(96) forward_first_split_kernel(const __grid_co
     splitLoadTile<M>(ws, N, lane, b, sel, in_ring, in_full, in_empty);
     return;
   }
-  const M model = model_in_constant_bank;
+  using LM = typename LatencyOf<M>::type;
+  const LM model(model_in_constant_bank);
   const S alpha = prm.alpha_list[0];
   if(warp == 0)
   {
     Matrix<S, NX, 1> x;
 #pragma unroll
     for(int d = 0; d < NX; d++) x[d] = ws.x[sel][(size_t)d * ws.Bp + b];
-    splitRollout<M, O::SIZE * kTile, kTile>(model, prm.t0, N, alpha, x, in_ring, lane, in_full, in_empty, out_ring + lane,
+    splitRollout<LM, O::SIZE * kTile, kTile>(model, prm.t0, N, alpha, x, in_ring, lane, in_full, in_empty, out_ring + lane,
                                             out_full, out_empty);
     return;
   }
   const bool work = active && prm.n_alpha > 0;
-  const S cost_new = splitCost<M>(model, prm.t0, N, out_ring + lane, out_full, out_empty, work, candidateBuffer<S>(ws, sel, b));
+  const S cost_new = splitCost<LM>(model, prm.t0, N, out_ring + lane, out_full, out_empty, work, candidateBuffer<S>(ws, sel, b));
   if(!active) return;
   const S cost_cur = ws.cost_sum[b];
   S actual = S(0), expected = S(0), ratio = S(0);
@@ -541,7 +542,8 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
   }
   if(warp > 2 * kFanWarps) return;
 
-  const M model = model_in_constant_bank;
+  using LM = typename LatencyOf<M>::type;
+  const LM model(model_in_constant_bank);
   const int pair = warp % kFanWarps;
   const int g = lane / GA;
   const int a = lane % GA;
@@ -560,7 +562,7 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
     Matrix<S, NX, 1> x;
 #pragma unroll
     for(int d = 0; d < NX; d++) x[d] = ws.x[sel][(size_t)d * Bp + b];
-    splitRollout<M, ROWS, 1>(model, prm.t0, N, my_alpha, x, sm.in_ring, inst * O::SIZE, sm.in_full, sm.in_empty, out_col,
+    splitRollout<LM, ROWS, 1>(model, prm.t0, N, my_alpha, x, sm.in_ring, inst * O::SIZE, sm.in_full, sm.in_empty, out_col,
                              sm.outFull(pair), sm.outEmpty(pair), in_base, out_base);
     return;
   }
@@ -568,7 +570,7 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
   // ------------------------------------------------------------------ cost warps
   const size_t item = (item_slot0 + (size_t)inst) * GA + a; // scratch column of this candidate
   const FwdDest<S> dst{fan.sx, fan.su, fan.sc, fan.items, item};
-  const S my_cost = splitCost<M>(model, prm.t0, N, out_col, sm.outFull(pair), sm.outEmpty(pair), work, dst, out_base);
+  const S my_cost = splitCost<LM>(model, prm.t0, N, out_col, sm.outFull(pair), sm.outEmpty(pair), work, dst, out_base);
 
   const S cost_cur = ws.cost_sum[b];
   S my_actual = S(0), my_expected = S(0), my_ratio = S(0);

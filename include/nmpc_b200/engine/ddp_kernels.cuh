@@ -91,6 +91,21 @@ struct Workspace
   int * fan_count; //!< [1] work-list length of the phased line search (reset by K0 / K1 / the fused K2)
 };
 
+/** The functor type a latency-bound kernel evaluates: `M::LatencyVariant` when the functor offers one (the same problem
+    and the same values, written for instruction latency rather than instruction count -- models/cartpole.h), else M.
+    The kernels that run one rollout per lane on a few warps per SM (ddp_forward_split.cuh, ddp_backward_lanes.cuh)
+    convert the functor they were launched with at entry; the throughput-bound kernels keep M. */
+template<class M, class = void>
+struct LatencyOf
+{
+  using type = M;
+};
+template<class M>
+struct LatencyOf<M, std::void_t<typename M::LatencyVariant>>
+{
+  using type = typename M::LatencyVariant;
+};
+
 /** Does the functor have a time-varying input dimension, `int inputDim(t)` <= NU (DDPProblem<StateDim, Eigen::Dynamic>,
     DDPProblem.h:61-85)?  Inputs a >= inputDim(t) are padding: kept at zero by K0 and decoupled by K1. */
 template<class M, class = void>

@@ -27,6 +27,23 @@ struct DdpRegistrar
   }
 };
 
+/** The functor's pointwise evaluation only (nmpc_b200_model_eval): no solver kernels are instantiated. */
+template<class M>
+struct EvalRegistrar
+{
+  explicit EvalRegistrar(const char * name)
+  {
+    ModelEntry & e = registryEntry(name);
+    e.nx = M::NX;
+    e.nu = M::NU;
+    e.ng = ineqDimOf<M>();
+    e.n_params = M::NUM_PARAMS;
+    e.default_params = [](double * p) { M::defaultParams(p); };
+    e.eval = [](const double * params, int dev, int n, const double * t, const double * x, const double * u,
+                const ModelEvalOutputs & out) { modelEval<M>(params, dev, n, t, x, u, out); };
+  }
+};
+
 template<class M>
 struct FmpcRegistrar
 {
@@ -55,3 +72,6 @@ struct FmpcRegistrar
 /** Make functor type MODEL (with ineqConst / calcIneqConstDeriv) available to nmpc_b200_fmpc_create() under NAME. */
 #define NMPC_B200_REGISTER_FMPC_MODEL(NAME, ...) \
   static ::nmpc_b200::FmpcRegistrar<__VA_ARGS__> NMPC_B200_CONCAT(nmpc_b200_fmpc_registrar_, __COUNTER__)(NAME)
+/** Make functor type MODEL available to nmpc_b200_model_eval() only (no solver can be created for NAME). */
+#define NMPC_B200_REGISTER_EVAL_ONLY(NAME, ...) \
+  static ::nmpc_b200::EvalRegistrar<__VA_ARGS__> NMPC_B200_CONCAT(nmpc_b200_eval_registrar_, __COUNTER__)(NAME)

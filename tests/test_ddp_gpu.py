@@ -65,6 +65,26 @@ def test_model_functor_matches_oracle(gpu):
     assert np.linalg.norm(d["Fx"][0] - Fx) < 1e-6
 
 
+def test_branch_free_device_math(gpu):
+    """models/cartpole.h: the functor written for instruction latency (CartPole<double, true>, what the lanes / split
+    kernels evaluate) gives the values of the library-math functor to the last bit over the range a rollout visits, and
+    NaN -- not a wrong number -- beyond |theta| = 2^31."""
+    rng = np.random.default_rng(11)
+    n = 4096
+    x = rng.uniform(-3, 3, (n, 4))
+    x[:, 1] = np.concatenate([rng.uniform(-10, 10, n // 2), rng.uniform(-1e6, 1e6, n // 4), rng.uniform(-2e9, 2e9, n // 4)])
+    x[0, 1], x[1, 1], x[2, 1] = 0.0, np.pi, -np.pi / 2
+    u = rng.uniform(-20, 20, (n, 1))
+    a = gpu.model_eval("cartpole", 0.0, x, u)
+    b = gpu.model_eval("cartpole_branch_free", 0.0, x, u)
+    for key in ("x_next", "Fx", "Fu", "Lx", "Lu", "running_cost"):
+        assert np.array_equal(a[key], b[key]), key
+    far = gpu.model_eval("cartpole_branch_free", 0.0, np.array([[0.0, 3e9, 0.0, 0.0]]), np.array([[1.0]]))
+    assert np.all(np.isnan(far["x_next"][0, 2:]))
+    with pytest.raises(gpu.NmpcB200Error):
+        gpu.DDPSolver("cartpole_branch_free", batch_capacity=1)  # evaluation only: no solver kernels behind that name
+
+
 def test_single_instance_swingup(gpu):
     """solve() of one instance: x0=(0,pi,0,0), N=100, max_iter=10 (oracle values pinned in test_oracle_ddp)."""
     solver = gpu.DDPSolver("cartpole", batch_capacity=1)
