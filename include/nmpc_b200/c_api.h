@@ -95,7 +95,9 @@ extern "C"
 
   /** Mirror of DDPSolver::Configuration (DDPSolver.h:47-110), same defaults.  print_level has no
       meaning for a batch; use_state_eq_second_derivative is rejected exactly where the reference
-      throws (DDPSolver.hpp:391-414). */
+      throws (DDPSolver.hpp:391-414).  ONE LIMIT the reference does not have: alpha_list holds at most 16 candidates
+      (the reference's std::vector takes any length, default 11) -- the line-search kernels evaluate the candidates of
+      an instance on the lanes of a half warp; a longer list is NMPC_B200_ERR_INVALID_ARGUMENT at set_config. */
   typedef struct
   {
     int horizon_steps; /* 100 */
@@ -197,6 +199,19 @@ extern "C"
       iter-0 entry (initial rollout in column 2), duration_forward = columns 2 + 3.  The batch runs every stage as one
       launch, so the durations of an iteration are those of the whole batch.  *rows_filled = entries available. */
   int nmpc_b200_ddp_get_iteration_durations(nmpc_b200_ddp * h, double * ms, int rows, int * rows_filled);
+
+  /** Kernel-selection knobs of a handle.  The engine picks, per stage, the kernel variant measured fastest for the
+      problem size on the device it runs on (thresholds scale with the device's SM count; DESIGN.md lists the variants
+      and the measurements); these calls read a knob or pin it, e.g. to reproduce an experiment or to re-tune for
+      another part.  Results do not depend on the choice beyond rounding.  Keys: backward_lanes (0 | 1 | 2),
+      backward_lanes_tiles_per_cta, backward_lanes_max_batch, backward_fused (0 | 1), backward_quad (-1 auto | 0 | 1),
+      backward_quad_max_batch, backward_group_size (-1 auto | 1 | 4 or 16), backward_coop_max_batch, backward_wide
+      (0 | 1), forward_lanes (-1 auto | 1 | 3 phased | 4 | 16), forward_phased_max_batch, forward_split (0 | 1),
+      forward_split_max_batch, threads_per_block (-1 auto | 32 .. 128), solve_tile (0 | 1), solve_tile_max_batch.
+      An unknown key is NMPC_B200_ERR_INVALID_ARGUMENT.  (Environment variables NMPC_B200_<KEY> preset a knob for
+      every handle of a process: a developer switch for the experiment scripts under tools/.) */
+  int nmpc_b200_ddp_set_tuning(nmpc_b200_ddp * h, const char * key, int value);
+  int nmpc_b200_ddp_get_tuning(nmpc_b200_ddp * h, const char * key, int * value);
 
   /* ------------------------------------------------------------------- user functors ---- */
 

@@ -11,6 +11,8 @@
 #pragma once
 
 #include <algorithm>
+#include <cctype>
+#include <string>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -76,6 +78,106 @@ inline void launchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
   NMPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 
+/** The engine's kernel-selection knobs (nmpc_b200_ddp_set_tuning / _get_tuning, c_api.h).  Defaults come from the
+    measurements on a 148-SM B200 recorded in DESIGN.md, scaled by the SM count of the device the engine runs on;
+    -1 = "decide from the problem size".  An environment variable NMPC_B200_<KEY IN CAPITALS> overrides a default at
+    construction (developer switch for tools/exp_variants.py); a call to setTuning overrides both. */
+struct DdpTuning
+{
+  int backward_lanes = 1; //!< n_x < 8, small batches: 0 thread per instance, 1 G lanes + smem exchange, 2 shuffles
+  int backward_lanes_tiles_per_cta = 1; //!< 32-instance tiles per CTA of the lanes kernel
+  int backward_lanes_max_batch = 0; //!< one tile per SM; beyond, the fused thread-per-instance sweep wins
+  int backward_fused = 1; //!< linearisation fused into the backward kernel (n_x < 8)
+  int backward_quad = -1; //!< four warps per tile (n_x >= 8): -1 by size, 0 never, 1 always
+  int backward_quad_max_batch = 0;
+  int backward_group_size = -1; //!< lanes per instance of the cooperative sweep: -1 by size, 1, or kCoopGS
+  int backward_coop_max_batch = 0;
+  int backward_wide = 1; //!< n_u >= 8 without limits: the n_u side spread over a lane group
+  int forward_lanes = -1; //!< -1 by size; 1 thread per instance; 4 / 16 lanes speculate; 3 = three-phase line search
+  int forward_phased_max_batch = 0;
+  int forward_split = 1; //!< phased line search with rollout / cost / loader warps
+  int forward_split_max_batch = 0;
+  int threads_per_block = -1;
+  int solve_tile = 0; //!< persistent CTA per tile for the whole solve (measured slower)
+  int solve_tile_max_batch = 0;
+  int sm_count = 148;
+
+  void scaleToDevice(int sms)
+  {
+    sm_count = sms;
+    backward_lanes_max_batch = sms * 32; // one 32-instance tile per SM
+    backward_quad_max_batch = sms * 4 * 32;
+    backward_coop_max_batch = sms * 128;
+    forward_phased_max_batch = sms * 332; // measured cross-over 49152 on 148 SMs
+    forward_split_max_batch = sms * 83; // measured cross-over 12288 on 148 SMs
+    solve_tile_max_batch = sms * 32;
+  }
+
+  /** Pointer to the knob called `key`, or nullptr. */
+  int * find(const std::string & key)
+  {
+#define NMPC_B200_TUNING_KEY(k) \
+  if(key == #k) return &k;
+    NMPC_B200_TUNING_KEY(backward_lanes)
+    NMPC_B200_TUNING_KEY(backward_lanes_tiles_per_cta)
+    NMPC_B200_TUNING_KEY(backward_lanes_max_batch)
+    NMPC_B200_TUNING_KEY(backward_fused)
+    NMPC_B200_TUNING_KEY(backward_quad)
+    NMPC_B200_TUNING_KEY(backward_quad_max_batch)
+    NMPC_B200_TUNING_KEY(backward_group_size)
+    NMPC_B200_TUNING_KEY(backward_coop_max_batch)
+    NMPC_B200_TUNING_KEY(backward_wide)
+    NMPC_B200_TUNING_KEY(forward_lanes)
+    NMPC_B200_TUNING_KEY(forward_phased_max_batch)
+    NMPC_B200_TUNING_KEY(forward_split)
+    NMPC_B200_TUNING_KEY(forward_split_max_batch)
+    NMPC_B200_TUNING_KEY(threads_per_block)
+    NMPC_B200_TUNING_KEY(solve_tile)
+    NMPC_B200_TUNING_KEY(solve_tile_max_batch)
+#undef NMPC_B200_TUNING_KEY
+    return nullptr;
+  }
+
+  static const char * const * keys(int & n)
+  {
+    static const char * const k[] = {"backward_lanes", "backward_lanes_tiles_per_cta", "backward_lanes_max_batch",
+                                     "backward_fused", "backward_quad", "backward_quad_max_batch", "backward_group_size",
+                                     "backward_coop_max_batch", "backward_wide", "forward_lanes", "forward_phased_max_batch",
+                                     "forward_split", "forward_split_max_batch", "threads_per_block", "solve_tile",
+                                     "solve_tile_max_batch"};
+    n = (int)(sizeof(k) / sizeof(k[0]));
+    return k;
+  }
+
+  /** NMPC_B200_<KEY> environment overrides (plus the older short names the experiment scripts use). */
+  void overlayEnvironment()
+  {
+    int n = 0;
+    const char * const * k = keys(n);
+    for(int i = 0; i < n; i++)
+    {
+      std::string name = "NMPC_B200_";
+      for(const char * c = k[i]; *c; c++) name += (char)std::toupper((unsigned char)*c);
+      if(const char * env = std::getenv(name.c_str())) *find(k[i]) = std::atoi(env);
+    }
+    static const char * const alias[][2] = {{"NMPC_B200_BWD_LANES", "backward_lanes"},
+                                            {"NMPC_B200_BWD_LANES_TPC", "backward_lanes_tiles_per_cta"},
+                                            {"NMPC_B200_BWD_LANES_MAXB", "backward_lanes_max_batch"},
+                                            {"NMPC_B200_BWD_FUSED", "backward_fused"},
+                                            {"NMPC_B200_BWD_QUAD", "backward_quad"},
+                                            {"NMPC_B200_BWD_GS", "backward_group_size"},
+                                            {"NMPC_B200_BWD_WIDE", "backward_wide"},
+                                            {"NMPC_B200_FWD_GA", "forward_lanes"},
+                                            {"NMPC_B200_FWD_SPLIT", "forward_split"},
+                                            {"NMPC_B200_FWD_SPLIT_MAXB", "forward_split_max_batch"},
+                                            {"NMPC_B200_TPB", "threads_per_block"},
+                                            {"NMPC_B200_TILE", "solve_tile"},
+                                            {"NMPC_B200_TILE_MAXB", "solve_tile_max_batch"}};
+    for(const auto & a : alias)
+      if(const char * env = std::getenv(a[0])) *find(a[1]) = std::atoi(env);
+  }
+};
+
 template<class M>
 class DdpEngine : public DdpEngineBase
 {
@@ -93,6 +195,10 @@ public:
     NMPC_CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     NMPC_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&h_counter_), sizeof(int)));
     Bp_ = ((capacity_ + 127) / 128) * 128;
+    int sms = 0;
+    NMPC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
+    tune_.scaleToDevice(sms);
+    tune_.overlayEnvironment();
     if(kThreadSweepFits)
     {
       NMPC_CUDA_CHECK(cudaFuncSetAttribute(backward_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -121,6 +227,24 @@ public:
   const nmpc_b200_ddp_config & config() const override
   {
     return cfg_;
+  }
+
+  void setTuning(const char * key, int value) override
+  {
+    int * knob = key ? tune_.find(key) : nullptr;
+    if(knob == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, std::string("unknown tuning key '") + (key ? key : "") + "'");
+    if(*knob == value) return;
+    DeviceGuard guard(device_);
+    *knob = value;
+    // the derivative buffers exist only for the unfused pipeline: the choice is made at allocation
+    if(use_fused_ != backwardUsesFused(capacity_)) allocate();
+  }
+
+  int getTuning(const char * key) override
+  {
+    int * knob = key ? tune_.find(key) : nullptr;
+    if(knob == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, std::string("unknown tuning key '") + (key ? key : "") + "'");
+    return *knob;
   }
 
   void setInputLimits(const double * lower, const double * upper) override
@@ -646,17 +770,11 @@ protected:
     NMPC_CUDA_CHECK(cudaGetLastError());
   }
 
-  static int envInt(const char * name, int dflt)
-  {
-    const char * env = std::getenv(name);
-    return env != nullptr ? std::atoi(env) : dflt;
-  }
-
   /** One persistent CTA per 32-instance tile for the whole solve (ddp_solve_tile.cuh): while every tile has an SM of
       its own.  Beyond that the tiles would queue up behind whole solves and the stage kernels take over. */
   bool usePersistent(int B) const
   {
-    return kLanesOk && use_fused_ && tile_variant_ != 0 && B <= tile_max_batch_;
+    return kLanesOk && use_fused_ && tune_.solve_tile != 0 && B <= tune_.solve_tile_max_batch;
   }
 
   void launchSolveTile(int B, cudaStream_t st)
@@ -716,34 +834,28 @@ protected:
 
   /** K3 variant: lanes per instance that evaluate line-search candidates concurrently.  Small
       batches cannot fill the 148 SMs with one thread per instance, so they spend lanes on speculation. */
-  static int forwardLanesPerInstance(int B)
+  int forwardLanesPerInstance(int B) const
   {
-    if(const char * env = std::getenv("NMPC_B200_FWD_GA"))
-    {
-      int v = std::atoi(env);
-      if(v == 1 || v == 4 || v == 16 || v == kPhased) return v;
-    }
+    const int v = tune_.forward_lanes;
+    if(v == 1 || v == 4 || v == 16 || v == kPhased) return v;
     // latency-bound regime: minimise the number of sequential rollouts.  Measured on B200 (cart-pole, M-fixed):
     // phased beats the in-warp fan-out up to B = 32768 (0.31 vs 0.37 ms) and loses at 131072 (1.18 vs 0.83 ms),
     // where evaluating all remaining candidates of every failed instance costs throughput.
-    if(B <= 49152) return kPhased;
+    if(B <= tune_.forward_phased_max_batch) return kPhased;
     return 1;
   }
 
   /** K2 variant: lanes per instance (columns of the n_x x n_x matrices are spread over the group). */
-  static int backwardLanesPerInstance(int B)
+  int backwardLanesPerInstance(int B) const
   {
     if(!kThreadSweepFits) return kCoopGS;
-    if(const char * env = std::getenv("NMPC_B200_BWD_GS"))
-    {
-      int v = std::atoi(env);
-      if(v == 1 || v == kCoopGS) return v;
-    }
+    const int v = tune_.backward_group_size;
+    if(v == 1 || v == kCoopGS) return v;
     // One thread per instance keeps every matrix in registers and is the faster variant while they fit
     // (measured on B200, cart-pole 4x1, B=4096: 84 us vs 113 us per sweep).  From n_x = 8 on the register
     // file overflows (n_x = 12: 19 KB of spills per thread) and the cooperative variant takes over.
     if(NX < 8) return 1;
-    return (B <= 148 * 128) ? kCoopGS : 1;
+    return (B <= tune_.backward_coop_max_batch) ? kCoopGS : 1;
   }
 
   template<bool CONSTRAINED>
@@ -766,21 +878,12 @@ protected:
   /** K1 + K2 fused (producer warp + consumer warp per 32-instance tile, ddp_backward_fused.cuh): the default while the
       thread-per-instance sweep is the K2 variant in use, i.e. for n_x < 8.  NMPC_B200_BWD_FUSED=0 restores the
       three-kernel pipeline. */
-  static bool backwardUsesFused(int B)
+  bool backwardUsesFused(int B) const
   {
     if(NX >= 8) return false;
-    if(const char * env = std::getenv("NMPC_B200_BWD_FUSED"))
-    {
-      if(env[0] == '0') return false;
-    }
-    if(const char * env = std::getenv("NMPC_B200_BWD_QUAD"))
-    {
-      if(env[0] == '1') return false;
-    }
-    if(const char * env = std::getenv("NMPC_B200_BWD_GS"))
-    {
-      if(std::atoi(env) > 1) return false;
-    }
+    if(tune_.backward_fused == 0) return false;
+    if(tune_.backward_quad == 1) return false;
+    if(tune_.backward_group_size > 1) return false;
     (void)B;
     return true;
   }
@@ -829,33 +932,30 @@ protected:
       using XS = XchSmem<S, LL::G>;
       using XH = XchShfl<S, LL::G>;
       const int c = CONSTRAINED ? 4 : 0;
-      if(lanes_variant_ == 2)
+      if(tune_.backward_lanes == 2)
       {
-        if(lanes_tiles_per_cta_ == 2) launchBackwardLanesT<CONSTRAINED, 2, XH, 2>(B, iter, st, c + 3);
+        if(tune_.backward_lanes_tiles_per_cta == 2) launchBackwardLanesT<CONSTRAINED, 2, XH, 2>(B, iter, st, c + 3);
         else launchBackwardLanesT<CONSTRAINED, 2, XH, 1>(B, iter, st, c + 2);
       }
       else
       {
-        if(lanes_tiles_per_cta_ == 2) launchBackwardLanesT<CONSTRAINED, 2, XS, 2>(B, iter, st, c + 1);
+        if(tune_.backward_lanes_tiles_per_cta == 2) launchBackwardLanesT<CONSTRAINED, 2, XS, 2>(B, iter, st, c + 1);
         else launchBackwardLanesT<CONSTRAINED, 2, XS, 1>(B, iter, st, c + 0);
       }
     }
   }
 
   /** K2 variant for latency-bound batches: four warps per 32-instance tile (ddp_backward_quad.cuh). */
-  static bool backwardUsesQuad(int B)
+  bool backwardUsesQuad(int B) const
   {
     if(QuadLayout<M>::bytes() > kQuadSmemLimit) return false;
-    if(const char * env = std::getenv("NMPC_B200_BWD_QUAD"))
-    {
-      if(env[0] == '0') return false;
-      if(env[0] == '1') return true;
-    }
+    if(tune_.backward_quad == 0) return false;
+    if(tune_.backward_quad == 1) return true;
     // Measured on B200: for n_x = 4 (cart-pole, B=4096) the three barriers per step cost what the split saves
     // (107 us vs 84 us per sweep; both variants are bound by one warp's dependent chain); for n_x = 12 (quadrotor
     // fp32, B=8192) the split beats both alternatives (14.5 ms vs 20.8 ms per 10 sweeps for the in-warp variant).
     if(NX < 8) return false;
-    return B <= 148 * 4 * 32;
+    return B <= tune_.backward_quad_max_batch;
   }
 
   template<bool CONSTRAINED>
@@ -878,13 +978,9 @@ protected:
       NMPC_B200_BWD_WIDE=0 falls back to the cooperative variant that recomputes the n_u x n_u part in every lane. */
   static constexpr int kWideGS = (NU <= 16 && NX < 16) ? 16 : 32;
   static constexpr bool kWideOk = NU >= 8 && NU <= kWideGS && NX < kWideGS;
-  static bool backwardUsesWide()
+  bool backwardUsesWide() const
   {
-    if(const char * env = std::getenv("NMPC_B200_BWD_WIDE"))
-    {
-      if(env[0] == '0') return false;
-    }
-    return kWideOk;
+    return kWideOk && tune_.backward_wide != 0;
   }
 
   void launchBackwardWide(int B, int iter, cudaStream_t st)
@@ -915,7 +1011,7 @@ protected:
     }
     if constexpr(NX < 8)
     {
-      if(use_fused_ && kLanesOk && lanes_variant_ != 0 && B <= lanes_max_batch_)
+      if(use_fused_ && kLanesOk && tune_.backward_lanes != 0 && B <= tune_.backward_lanes_max_batch)
       {
         if(cfg_.with_input_constraint)
           launchBackwardLanes<true>(B, iter, st);
@@ -981,7 +1077,7 @@ protected:
     // the split rings (two steps per stage) must fit an SM's shared memory: not for many inputs (centroidal motion 9 x 16)
     constexpr size_t kSplitFirstBytes = sizeof(S) * (SplitLayout<M>::inElems(kTile) + SplitLayout<M>::outElems(kTile)) + 256;
     constexpr bool kSplitFits = kSplitFirstBytes <= 200 * 1024 && FanSmem<M>::bytes() <= 200 * 1024;
-    const bool split = kSplitFits && fwd_split_ != 0 && B <= fwd_split_max_batch_;
+    const bool split = kSplitFits && tune_.forward_split != 0 && B <= tune_.forward_split_max_batch;
     if(split)
     {
       // one 32-instance tile per CTA: rollout warp + cost warp + loader warp (ddp_forward_split.cuh)
@@ -1074,17 +1170,14 @@ protected:
     return tpb;
   }
 
-  static int threadsPerBlock(int B)
+  int threadsPerBlock(int B) const
   {
     const int cap = maxThreadsPerBlock();
-    if(const char * env = std::getenv("NMPC_B200_TPB"))
-    {
-      int v = std::atoi(env);
-      if(v >= 32 && v <= cap && v % 32 == 0) return v;
-    }
-    // spread small batches over all 148 SMs: one warp per CTA until every SM has a few warps
-    if(B <= 148 * 32 * 2) return 32;
-    if(B <= 148 * 64 * 4) return std::min(64, cap);
+    const int v = tune_.threads_per_block;
+    if(v >= 32 && v <= cap && v % 32 == 0) return v;
+    // spread small batches over all SMs: one warp per CTA until every SM has a few warps
+    if(B <= tune_.sm_count * 32 * 2) return 32;
+    if(B <= tune_.sm_count * 64 * 4) return std::min(64, cap);
     return std::min(128, cap);
   }
 
@@ -1234,17 +1327,11 @@ protected:
   bool attr_set_[10] = {false, false, false, false, false, false, false, false, false, false};
   bool use_fused_ = false; //!< K1 fused into K2 (decided once, at allocation)
   bool lanes_attr_set_[12] = {};
-  int lanes_variant_ = envInt("NMPC_B200_BWD_LANES", 1); //!< 0: thread per instance, 1: G lanes, smem exchange, 2: shuffles
-  int lanes_tiles_per_cta_ = envInt("NMPC_B200_BWD_LANES_TPC", 1); //!< 32-instance tiles per CTA
-  int tile_variant_ = envInt("NMPC_B200_TILE", 0); //!< 1: persistent CTA per tile while B <= tile_max_batch_ (measured slower)
-  int tile_max_batch_ = envInt("NMPC_B200_TILE_MAXB", 148 * kTile);
+  DdpTuning tune_;
   bool tile_attr_set_[2] = {false, false};
   bool persistent_last_ = false; //!< the last solve ran in the persistent kernel
   bool persistent_timed_ = false;
   DeviceBuffer<unsigned long long> stage_ns_;
-  int fwd_split_ = envInt("NMPC_B200_FWD_SPLIT", 1); //!< line search with rollout / cost / loader warps
-  int fwd_split_max_batch_ = envInt("NMPC_B200_FWD_SPLIT_MAXB", 12288); //!< measured: 0.94 vs 1.03 ms at 8192, 1.63 vs 1.58 at 16384
-  int lanes_max_batch_ = envInt("NMPC_B200_BWD_LANES_MAXB", 148 * kTile); //!< one tile per SM; beyond, the thread-per-instance sweep wins
   bool limits_vary_ = false; //!< the limits differ between horizon steps
   bool timing_ = false;
   std::vector<cudaEvent_t> events_;

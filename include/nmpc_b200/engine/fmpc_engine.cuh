@@ -41,6 +41,7 @@ public:
     NMPC_CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     NMPC_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void **>(&h_flag_), sizeof(int)));
     Bp_ = ((capacity_ + 127) / 128) * 128;
+    NMPC_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
     applyConfig(cfg, true);
   }
 
@@ -424,15 +425,17 @@ protected:
     NMPC_CUDA_CHECK(cudaGetLastError());
   }
 
-  static int threadsPerBlock(int B)
+  /** One warp per CTA until every SM has a few warps, then larger CTAs (NMPC_B200_THREADS_PER_BLOCK pins it). */
+  int threadsPerBlock(int B) const
   {
-    if(const char * env = std::getenv("NMPC_B200_TPB"))
-    {
-      int v = std::atoi(env);
-      if(v >= 32 && v <= 128 && v % 32 == 0) return v;
-    }
-    if(B <= 148 * 32 * 2) return 32;
-    if(B <= 148 * 64 * 4) return 64;
+    static const int pinned = [] {
+      const char * env = std::getenv("NMPC_B200_THREADS_PER_BLOCK");
+      if(env == nullptr) env = std::getenv("NMPC_B200_TPB");
+      return env != nullptr ? std::atoi(env) : -1;
+    }();
+    if(pinned >= 32 && pinned <= 128 && pinned % 32 == 0) return pinned;
+    if(B <= sm_count_ * 32 * 2) return 32;
+    if(B <= sm_count_ * 64 * 4) return 64;
     return 128;
   }
 
@@ -526,6 +529,7 @@ protected:
   M model_;
   int device_;
   int capacity_;
+  int sm_count_ = 148;
   int Bp_ = 0;
   int B_ = 0;
   nmpc_b200_fmpc_config cfg_{};

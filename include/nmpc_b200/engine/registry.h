@@ -52,6 +52,8 @@ public:
   virtual void enableTiming(bool enable) = 0;
   virtual void getDurations(double * ms, int * launches) = 0;
   virtual int getIterationDurations(double * ms, int rows) = 0;
+  virtual void setTuning(const char * key, int value) = 0;
+  virtual int getTuning(const char * key) = 0;
 };
 
 /** Batched FMPC solver bound to one functor type. */

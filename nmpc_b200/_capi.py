@@ -93,6 +93,7 @@ EXPORTED_SYMBOLS = [
     "nmpc_b200_fmpc_config_default", "nmpc_b200_fmpc_create", "nmpc_b200_fmpc_destroy", "nmpc_b200_fmpc_set_config",
     "nmpc_b200_fmpc_solve", "nmpc_b200_fmpc_get", "nmpc_b200_fmpc_sync", "nmpc_b200_fmpc_enable_timing",
     "nmpc_b200_fmpc_get_durations", "nmpc_b200_fmpc_run_mpc",
+    "nmpc_b200_ddp_set_tuning", "nmpc_b200_ddp_get_tuning",
     "nmpc_b200_ddp_create_sharded", "nmpc_b200_ddp_sharded_destroy", "nmpc_b200_ddp_sharded_num_shards",
     "nmpc_b200_ddp_sharded_shard", "nmpc_b200_ddp_sharded_range", "nmpc_b200_ddp_sharded_set_config",
     "nmpc_b200_ddp_sharded_set_input_limits", "nmpc_b200_ddp_sharded_solve", "nmpc_b200_ddp_sharded_get",
@@ -137,6 +138,8 @@ def lib():
         L.nmpc_b200_load_plugin.argtypes = [C.c_char_p]
         L.nmpc_b200_ddp_set_input_limits_mpc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.nmpc_b200_ddp_get_iteration_durations.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.nmpc_b200_ddp_set_tuning.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.nmpc_b200_ddp_get_tuning.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.nmpc_b200_ddp_create_sharded.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                                    C.c_int, C.c_void_p]
         L.nmpc_b200_ddp_sharded_destroy.argtypes = [C.c_void_p]

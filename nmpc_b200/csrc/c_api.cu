@@ -348,6 +348,23 @@ int nmpc_b200_ddp_get(nmpc_b200_ddp * h, int what, void * dst, size_t dst_bytes,
   });
 }
 
+int nmpc_b200_ddp_set_tuning(nmpc_b200_ddp * h, const char * key, int value)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_HANDLE(h);
+    h->engine->setTuning(key, value);
+  });
+}
+
+int nmpc_b200_ddp_get_tuning(nmpc_b200_ddp * h, const char * key, int * value)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_HANDLE(h);
+    if(value == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null value");
+    *value = h->engine->getTuning(key);
+  });
+}
+
 int nmpc_b200_ddp_sync(nmpc_b200_ddp * h)
 {
   return guarded([&] {

@@ -330,6 +330,16 @@ class DDPSolver:
         """Copy field `what` into a preallocated numpy array or float64 torch CUDA tensor."""
         return self._get_f64(what, tuple(out.shape), out=out, stream=stream)
 
+    def set_tuning(self, **knobs):
+        """Pin kernel-selection knobs (nmpc_b200_ddp_set_tuning), e.g. ``set_tuning(backward_lanes=0, forward_split=0)``."""
+        for key, value in knobs.items():
+            check(lib().nmpc_b200_ddp_set_tuning(self._h, key.encode(), int(value)))
+
+    def get_tuning(self, key):
+        v = C.c_int()
+        check(lib().nmpc_b200_ddp_get_tuning(self._h, key.encode(), C.byref(v)))
+        return v.value
+
     def get_to_device_ptr(self, what, ptr, nbytes, stream=None):
         """Field `what` into device memory given as a raw address -- e.g. a row of a sharding.PeerBuffer that lives on
         another GPU / in another process: the gather kernel stores straight into it."""

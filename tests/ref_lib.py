@@ -14,7 +14,7 @@ import oracle_lib as O
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _REF_DIR = os.path.join(_ROOT, "oracle", "ref")
 _LIB = os.path.join(_ROOT, "oracle", "_ref", "libnmpc_ref.so")
-REFERENCE_ROOT = "/root/reference"
+REFERENCE_ROOT = os.environ.get("REF", "/root/reference")  # the same variable oracle/ref/Makefile reads
 
 
 def available():
@@ -29,7 +29,7 @@ def lib():
     if _lib is None:
         if not available():
             raise RuntimeError("the reference checkout is not present on this machine")
-        subprocess.run(["make", "-s", "-C", _REF_DIR], check=True)
+        subprocess.run(["make", "-s", "-C", _REF_DIR, f"REF={REFERENCE_ROOT}"], check=True)
         _lib = C.CDLL(_LIB)
     return _lib
 

@@ -85,6 +85,36 @@ def test_branch_free_device_math(gpu):
         gpu.DDPSolver("cartpole_branch_free", batch_capacity=1)  # evaluation only: no solver kernels behind that name
 
 
+def test_tuning_knobs(gpu):
+    """nmpc_b200_ddp_set_tuning / _get_tuning: defaults scale with the device's SM count, a pinned variant solves the same
+    problem (to rounding), unknown keys are refused."""
+    import torch
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, N = 512, 60
+    x0 = O.cartpole_x0(B, 31)
+    s = gpu.DDPSolver("cartpole", batch_capacity=B)
+    s.config().horizon_steps, s.config().max_iter = N, 6
+    assert s.get_tuning("backward_lanes_max_batch") == sms * 32
+    assert s.get_tuning("forward_split_max_batch") == sms * 83 and s.get_tuning("forward_phased_max_batch") == sms * 332
+    s.solve_batch(0.0, x0, np.zeros((B, N, 1)))
+    u_default, cost_default = s.controlData().u_list, s.cost()
+    for knobs in (dict(backward_lanes=0), dict(backward_lanes=2), dict(backward_fused=0), dict(forward_split=0),
+                  dict(forward_lanes=1), dict(backward_lanes_max_batch=256, forward_split_max_batch=256)):
+        t = gpu.DDPSolver("cartpole", batch_capacity=B)
+        t.config().horizon_steps, t.config().max_iter = N, 6
+        t.set_tuning(**knobs)
+        assert all(t.get_tuning(k) == v for k, v in knobs.items())
+        t.solve_batch(0.0, x0, np.zeros((B, N, 1)))
+        assert np.array_equal(t.iterations(), s.iterations()), knobs
+        np.testing.assert_allclose(t.cost(), cost_default, rtol=1e-10, err_msg=str(knobs))
+        assert np.max(np.abs(t.controlData().u_list - u_default)) <= 1e-7 * (1 + np.max(np.abs(u_default))), knobs
+        t.close()
+    with pytest.raises(gpu.NmpcB200Error):
+        s.set_tuning(no_such_knob=1)
+    s.close()
+
+
 def test_single_instance_swingup(gpu):
     """solve() of one instance: x0=(0,pi,0,0), N=100, max_iter=10 (oracle values pinned in test_oracle_ddp)."""
     solver = gpu.DDPSolver("cartpole", batch_capacity=1)
