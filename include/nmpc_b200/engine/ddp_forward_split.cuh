@@ -69,8 +69,10 @@ __device__ __forceinline__ void splitRollout(const M & model,
   using O = FwdOperands<NX, NU>;
   constexpr int OUT = NX + NU;
   const S dt = model.dt();
+  static_assert(kSPS == 2, "RolloutCarry prepares two steps at a time");
+  RolloutCarry<M> carry;
 
-  auto step = [&](const S * op, S * oc, S t) {
+  auto step = [&](const S * op, S * oc, S t, int q) {
     S xr[NX], ur[NU], kr[NU], Kr[NU * NX];
 #pragma unroll
     for(int d = 0; d < NX; d++) xr[d] = op[(size_t)(O::X + d) * IN_ES];
@@ -110,7 +112,7 @@ __device__ __forceinline__ void splitRollout(const M & model,
     for(int d = 0; d < NX; d++) oc[(size_t)d * kTile] = x[d];
 #pragma unroll
     for(int d = 0; d < NU; d++) oc[(size_t)(NX + d) * kTile] = u[d];
-    x = model.stateEq(t, x, u);
+    x = carry.advance(model, t, x, u, q);
   };
 
   const int n_pairs = N / kSPS;
@@ -120,12 +122,13 @@ __device__ __forceinline__ void splitRollout(const M & model,
   {
     const unsigned gi = in_base + (unsigned)g, go = out_base + (unsigned)g;
     const unsigned st = gi % kSplitIn, so = go % kSplitOut;
+    carry.prepare(model, t0 + fi * dt, x); // both steps' trigonometry, side by side (placing it after the waits: same time)
     mbarWait(&in_full[st], (gi / kSplitIn) & 1u);
     if(go >= (unsigned)kSplitOut) mbarWait(&out_empty[so], ((go / kSplitOut) - 1u) & 1u);
     const S * op = in_ring + (size_t)st * kSPS * IN_STAGE + in_off;
     S * oc = out_col + (size_t)so * kSPS * OUT * kTile;
 #pragma unroll
-    for(int q = 0; q < kSPS; q++) step(op + (size_t)q * IN_STAGE, oc + (size_t)q * OUT * kTile, t0 + (fi + S(q)) * dt);
+    for(int q = 0; q < kSPS; q++) step(op + (size_t)q * IN_STAGE, oc + (size_t)q * OUT * kTile, t0 + (fi + S(q)) * dt, q);
     mbarArrive(&in_empty[st]);
     mbarArrive(&out_full[so]);
   }
@@ -140,7 +143,8 @@ __device__ __forceinline__ void splitRollout(const M & model,
     {
       const unsigned st = gi % kSplitIn;
       mbarWait(&in_full[st], (gi / kSplitIn) & 1u);
-      step(in_ring + (size_t)st * kSPS * IN_STAGE + in_off, oc, t0 + fi * dt);
+      carry.prepare(model, t0 + fi * dt, x);
+      step(in_ring + (size_t)st * kSPS * IN_STAGE + in_off, oc, t0 + fi * dt, 0);
       mbarArrive(&in_empty[st]);
       q = 1;
     }

@@ -92,7 +92,7 @@ struct Workspace
 };
 
 /** The functor type a latency-bound kernel evaluates: `M::LatencyVariant` when the functor offers one (the same problem
-    and the same values, written for instruction latency rather than instruction count -- models/cartpole.h), else M.
+    and the same values to within rounding, written for instruction latency rather than instruction count -- models/cartpole.h), else M.
     The kernels that run one rollout per lane on a few warps per SM (ddp_forward_split.cuh, ddp_backward_lanes.cuh)
     convert the functor they were launched with at entry; the throughput-bound kernels keep M. */
 template<class M, class = void>
@@ -104,6 +104,49 @@ template<class M>
 struct LatencyOf<M, std::void_t<typename M::LatencyVariant>>
 {
   using type = typename M::LatencyVariant;
+};
+
+/** Does the functor split stateEq into statePrePair / stateEqPre (models/cartpole.h), so that a rollout can take the
+    expensive functions of the state out of its step-to-step dependency chain? */
+template<class M, class = void>
+struct HasStatePre : std::false_type
+{
+};
+template<class M>
+struct HasStatePre<M, std::void_t<typename M::StatePre>> : std::true_type
+{
+};
+/** What a rollout that advances two steps at a time carries besides the state: prepare(x) before the pair, then
+    advance(.., 0) and advance(.., 1). */
+template<class M, bool = HasStatePre<M>::value>
+struct RolloutCarry
+{
+  __device__ __forceinline__ void prepare(const M &, typename M::Scalar, const typename M::StateDimVector &) {}
+  __device__ __forceinline__ typename M::StateDimVector advance(const M & model,
+                                                                typename M::Scalar t,
+                                                                const typename M::StateDimVector & x,
+                                                                const typename M::InputDimVector & u,
+                                                                int)
+  {
+    return model.stateEq(t, x, u);
+  }
+};
+template<class M>
+struct RolloutCarry<M, true>
+{
+  typename M::StatePre pre[2];
+  __device__ __forceinline__ void prepare(const M & model, typename M::Scalar t, const typename M::StateDimVector & x)
+  {
+    model.statePrePair(t, x, pre[0], pre[1]);
+  }
+  __device__ __forceinline__ typename M::StateDimVector advance(const M & model,
+                                                                typename M::Scalar t,
+                                                                const typename M::StateDimVector & x,
+                                                                const typename M::InputDimVector & u,
+                                                                int q)
+  {
+    return model.stateEqPre(t, x, u, pre[q]);
+  }
 };
 
 /** Does the functor have a time-varying input dimension, `int inputDim(t)` <= NU (DDPProblem<StateDim, Eigen::Dynamic>,
