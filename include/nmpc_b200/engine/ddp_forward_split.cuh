@@ -572,8 +572,15 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
   }
 
   // ------------------------------------------------------------------ cost warps
-  const size_t item = (item_slot0 + (size_t)inst) * GA + a; // scratch column of this candidate
-  const FwdDest<S> dst{fan.sx, fan.su, fan.sc, fan.items, item};
+  // Scratch of this listed slot: ONE contiguous block [row][candidate] per part (x, u, cost), so that the winner's rows
+  // are 128 bytes apart when the group copies them out -- with the batch-innermost layout of the main buffers every row
+  // of a candidate sat 16 * Bp * 8 bytes from the next one (a different 2 MB page per few rows: the copy was 16 % of the
+  // kernel's samples, one stalled store).
+  const size_t scratch_slot = item_slot0 + (size_t)inst;
+  const size_t rows_x_all = (size_t)(N + 1) * NX, rows_u_all = (size_t)N * NU, rows_c_all = (size_t)(N + 1);
+  const FwdDest<S> dst{fan.sx + scratch_slot * rows_x_all * GA, fan.su + scratch_slot * rows_u_all * GA,
+                       fan.sc + scratch_slot * rows_c_all * GA,
+                       (size_t)GA, (size_t)a};
   const S my_cost = splitCost<LM>(model, prm.t0, N, out_col, sm.outFull(pair), sm.outEmpty(pair), work, dst, out_base);
 
   const S cost_cur = ws.cost_sum[b];
@@ -601,23 +608,22 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
   __syncwarp();
   if(success)
   {
-    const size_t win = (item_slot0 + (size_t)inst) * GA + pick;
     const int rows_x = (N + 1) * NX, rows_u = N * NU, rows_c = N + 1;
     S * dx = ws.x[sel ^ 1];
     S * du = ws.u[sel ^ 1];
     S * dc = ws.cost[sel ^ 1];
     const int rows = rows_x + rows_u + rows_c;
     auto src = [&](int r) -> const S * {
-      return (r < rows_x) ? fan.sx + (size_t)r * fan.items + win
-                          : (r < rows_x + rows_u) ? fan.su + (size_t)(r - rows_x) * fan.items + win
-                                                  : fan.sc + (size_t)(r - rows_x - rows_u) * fan.items + win;
+      return (r < rows_x) ? dst.x + (size_t)r * GA + pick
+                          : (r < rows_x + rows_u) ? dst.u + (size_t)(r - rows_x) * GA + pick
+                                                  : dst.c + (size_t)(r - rows_x - rows_u) * GA + pick;
     };
     auto dstp = [&](int r) -> S * {
       return (r < rows_x) ? dx + (size_t)r * Bp + b
                           : (r < rows_x + rows_u) ? du + (size_t)(r - rows_x) * Bp + b
                                                   : dc + (size_t)(r - rows_x - rows_u) * Bp + b;
     };
-    constexpr int kInFlight = 16;
+    constexpr int kInFlight = 40; // one round trip for a 100-step cart-pole trajectory (605 rows over 16 lanes)
     for(int r0 = a; r0 < rows; r0 += GA * kInFlight)
     {
       S v[kInFlight];
