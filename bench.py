@@ -306,6 +306,8 @@ def ddp_roofline(wl, B, value_per_gpu, solver, iter_ms, launches, peak, peak_src
     listed = rows & (tr[:, 1:, 4] != alpha0) & (tr[:, 1:, 4] != 0.0)
     winners = listed & (tr[:, 1:, 1] != tr[:, :-1, 1])
     n_iter_launch = max(int(iters.max()), 1)
+    # an iteration that ends in the small-gradient test runs no line search (M-ref): n_fwd may be below iters
+    first_passes = np.minimum(iters, n_fwd)
     fused = launches["derivative"] == 0
     per = {k: float(np.mean(iter_ms[1:n_iter_launch + 1, c])) for k, c in
            (("derivative", 0), ("backward", 1), ("forward_first", 2), ("forward_rest", 3))}
@@ -316,14 +318,14 @@ def ddp_roofline(wl, B, value_per_gpu, solver, iter_ms, launches, peak, peak_src
     compulsory = {
         "derivative": sz * el["D1"] * float(iters.sum()) / n_iter_launch,
         "backward": sz * (el["fused_bwd"] if fused else el["D2"]) * float(n_bwd.sum()) / n_iter_launch,
-        "forward_first": sz * el["D3"] * float(iters.sum()) / n_iter_launch,
+        "forward_first": sz * el["D3"] * float(first_passes.sum()) / n_iter_launch,
         "forward_rest": sz * (el["fan_read"] * float(listed.sum()) + el["fan_write"] * float(winners.sum())) / n_iter_launch,
     }
     survey = {
         "derivative": compulsory["derivative"],
         "backward": sz * ((el["D1"] + el["D2"]) if fused else el["D2"]) * float(n_bwd.sum()) / n_iter_launch,
         "forward_first": compulsory["forward_first"],
-        "forward_rest": sz * el["D3"] * float(n_fwd.sum() - iters.sum()) / n_iter_launch,
+        "forward_rest": sz * el["D3"] * float((n_fwd - first_passes).sum()) / n_iter_launch,
     }
     names = {
         "derivative": "ddp::linearize_kernel",
@@ -354,7 +356,7 @@ def ddp_roofline(wl, B, value_per_gpu, solver, iter_ms, launches, peak, peak_src
         except Exception:
             traffic = None
     traj_comp = sz * (el["D0"] + (el["fused_bwd"] if fused else el["D1"] + el["D2"]) * float(n_bwd.sum()) / B
-                      + el["D3"] * float(iters.sum()) / B
+                      + el["D3"] * float(first_passes.sum()) / B
                       + (el["fan_read"] * float(listed.sum()) + el["fan_write"] * float(winners.sum())) / B)
     traj_survey = sz * (el["D0"] + (el["D1"] + el["D2"]) * float(n_bwd.sum()) / B + el["D3"] * float(n_fwd.sum()) / B)
     return {

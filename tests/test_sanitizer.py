@@ -1,6 +1,6 @@
 """compute-sanitizer over the hand-synchronised kernels (mbarrier rings between producer / loader / consumer warps,
 cp.async + mbarrier.arrive.noinc, group barriers, the lambda-retry votes): memcheck, synccheck and racecheck must
-report nothing on tools/sanitize_cases.py.  Logs of the round's runs are kept under profiles/ (r2_sanitizer_*.txt)."""
+report nothing on tools/sanitize_cases.py.  Logs of the round's last run are kept under profiles/r2_sanitizer/ (summary: profiles/r2_sanitizer.md)."""
 import os
 import shutil
 import subprocess
