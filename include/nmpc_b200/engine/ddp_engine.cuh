@@ -736,7 +736,22 @@ protected:
     }
     const int tpb = threadsPerBlock(B);
     const int grid = (B + tpb - 1) / tpb;
-    launchPdl(rollout_init_kernel<M>, dim3(grid), dim3(tpb), 0, st, model_, ws_, prm_);
+    if(initialRolloutUsesSplit(B))
+    {
+      // the line search's rollout / cost / loader roles (ddp_forward_split.cuh): 39 -> 27 us at B = 4096
+      using SL = SplitLayout<M>;
+      const size_t smem = sizeof(S) * (SL::inElems(kTile) + SL::outElems(kTile))
+                          + sizeof(unsigned long long) * 2 * (kSplitIn + kSplitOut) + 16;
+      bool & attr_set = init_split_attr_set_;
+      if(!attr_set)
+      {
+        NMPC_CUDA_CHECK(cudaFuncSetAttribute(rollout_init_split_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      launchPdl(rollout_init_split_kernel<M>, dim3((B + kTile - 1) / kTile), dim3(96), smem, st, model_, ws_, prm_);
+    }
+    else
+      launchPdl(rollout_init_kernel<M>, dim3(grid), dim3(tpb), 0, st, model_, ws_, prm_);
     launches_[0]++;
     record(st); // 2: setup done
 
@@ -1069,14 +1084,23 @@ protected:
     launchPdl(forward_spec_kernel<M, GA>, dim3(grid), dim3(kWarps * 32), smem, st, model_, ws_, prm_, iter);
   }
 
+  // the split rings (two steps per stage) must fit an SM's shared memory: not for many inputs (centroidal motion 9 x 16)
+  static constexpr size_t kSplitFirstBytes = sizeof(S) * (SplitLayout<M>::inElems(kTile) + SplitLayout<M>::outElems(kTile)) + 256;
+  static constexpr bool kSplitFits = kSplitFirstBytes <= 200 * 1024 && FanSmem<M>::bytes() <= 200 * 1024;
+
+  /** K0 in the split-role form: same regime as the split line search (a functor with a time-varying input dimension
+      keeps the thread-per-instance K0, whose padding rule it shares with the MPC-loop kernel). */
+  bool initialRolloutUsesSplit(int B) const
+  {
+    return kSplitFits && !HasInputDim<M>::value && tune_.forward_split != 0 && B <= tune_.forward_split_max_batch
+           && forwardLanesPerInstance(B) == kPhased;
+  }
+
   /** Three-phase line search (ddp_forward_phased.cuh). */
   void launchForwardPhased(int B, int iter, cudaStream_t st)
   {
     using O = FwdOperands<NX, NU>;
     ensureFanout();
-    // the split rings (two steps per stage) must fit an SM's shared memory: not for many inputs (centroidal motion 9 x 16)
-    constexpr size_t kSplitFirstBytes = sizeof(S) * (SplitLayout<M>::inElems(kTile) + SplitLayout<M>::outElems(kTile)) + 256;
-    constexpr bool kSplitFits = kSplitFirstBytes <= 200 * 1024 && FanSmem<M>::bytes() <= 200 * 1024;
     const bool split = kSplitFits && tune_.forward_split != 0 && B <= tune_.forward_split_max_batch;
     if(split)
     {
@@ -1327,6 +1351,7 @@ protected:
   bool attr_set_[10] = {false, false, false, false, false, false, false, false, false, false};
   bool use_fused_ = false; //!< K1 fused into K2 (decided once, at allocation)
   bool lanes_attr_set_[12] = {};
+  bool init_split_attr_set_ = false;
   DdpTuning tune_;
   bool tile_attr_set_[2] = {false, false};
   bool persistent_last_ = false; //!< the last solve ran in the persistent kernel

@@ -395,6 +395,79 @@ __global__ void __launch_bounds__(96) forward_first_split_kernel(const __grid_co
   fan.list[slot] = b;
 }
 
+/** K0 with the same three roles (solve()'s initial rollout, DDPSolver.hpp:36-38, :83-104): the given inputs as they
+    are, costs and trajectory into buffer 0, lambda / dlambda / counters reset, iter-0 trace entry.  The loader streams
+    the whole operand tile although only u_i is used (k, K rows hold whatever the previous solve left: never read by
+    the INIT rollout). */
+template<class M>
+__global__ void __launch_bounds__(96) rollout_init_split_kernel(const __grid_constant__ M model_in_constant_bank,
+                                                                 const __grid_constant__ Workspace<typename M::Scalar> ws,
+                                                                 const __grid_constant__ SolverParams<typename M::Scalar> prm)
+{
+  pdlPrologue();
+  using S = typename M::Scalar;
+  constexpr int NX = M::NX;
+  using SL = SplitLayout<M>;
+  using O = typename SL::O;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S * in_ring = reinterpret_cast<S *>(smem_raw);
+  S * out_ring = in_ring + SL::inElems(kTile);
+  unsigned long long * in_full = reinterpret_cast<unsigned long long *>(out_ring + SL::outElems(kTile));
+  unsigned long long * in_empty = in_full + kSplitIn;
+  unsigned long long * out_full = in_empty + kSplitIn;
+  unsigned long long * out_empty = out_full + kSplitOut;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if(threadIdx.x == 0)
+  {
+    for(int st = 0; st < kSplitIn; st++)
+    {
+      mbarInit(&in_full[st], 32);
+      mbarInit(&in_empty[st], 32);
+    }
+    for(int st = 0; st < kSplitOut; st++)
+    {
+      mbarInit(&out_full[st], 32);
+      mbarInit(&out_empty[st], 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    if(blockIdx.x == 0) *ws.fan_count = 0;
+  }
+  __syncthreads();
+  const int bg = blockIdx.x * kTile + lane;
+  const int b = (bg < ws.B) ? bg : (ws.B - 1);
+  const bool mine = bg < ws.B;
+  const int N = prm.N;
+  if(warp == 2)
+  {
+    splitLoadTile<M>(ws, N, lane, b, 0, in_ring, in_full, in_empty);
+    return;
+  }
+  using LM = typename LatencyOf<M>::type;
+  const LM model(model_in_constant_bank);
+  if(warp == 0)
+  {
+    Matrix<S, NX, 1> x;
+#pragma unroll
+    for(int d = 0; d < NX; d++) x[d] = ws.x[0][(size_t)d * ws.Bp + b];
+    splitRollout<LM, O::SIZE * kTile, kTile, true>(model, prm.t0, N, S(0), x, in_ring, lane, in_full, in_empty, out_ring + lane,
+                                                  out_full, out_empty);
+    return;
+  }
+  const FwdDest<S> dst{ws.x[0], ws.u[0], ws.cost[0], (size_t)ws.Bp, (size_t)b};
+  const S csum = splitCost<LM>(model, prm.t0, N, out_ring + lane, out_full, out_empty, mine, dst);
+  if(!mine) return;
+  ws.lambda[b] = prm.initial_lambda;
+  ws.dlambda[b] = prm.initial_dlambda;
+  ws.cost_sum[b] = csum;
+  ws.status[b] = 0;
+  ws.sel[b] = 0;
+  ws.iters[b] = 0;
+  ws.n_fwd[b] = 0;
+  ws.n_bwd[b] = 0;
+  writeTrace<S>(ws, b, 0, S(0), csum, prm.initial_lambda, prm.initial_dlambda, S(0), S(0), S(0), S(0), S(0));
+}
+
 /** Shared-memory carve-up of phase 2: one broadcast in-ring for the CTA's eight listed instances and one out-ring per
     rollout / cost warp pair. */
 template<class M>
