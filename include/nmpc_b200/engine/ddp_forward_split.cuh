@@ -698,7 +698,11 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
                           : (r < rows_x + rows_u) ? du + (size_t)(r - rows_x) * Bp + b
                                                   : dc + (size_t)(r - rows_x - rows_u) * Bp + b;
     };
-    constexpr int kInFlight = 40; // one round trip for a 100-step cart-pole trajectory (605 rows over 16 lanes)
+    // One round trip for a 100-step cart-pole trajectory (605 rows over 16 lanes).  In-kernel time stamps put this
+    // copy at 6-8 us of the kernel's 38: it is bound by the LSU's sector rate -- every 8-byte element, read or written,
+    // is alone in its 32-byte sector (4840 + 4840 sectors per CTA) -- not by instructions or latency: three rounds of
+    // cheaply addressed loads (running pointers) were no faster (39.4 us) than this single round.
+    constexpr int kInFlight = 40;
     for(int r0 = a; r0 < rows; r0 += GA * kInFlight)
     {
       S v[kInFlight];
