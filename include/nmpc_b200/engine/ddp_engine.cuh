@@ -1086,7 +1086,7 @@ protected:
 
   // the split rings (two steps per stage) must fit an SM's shared memory: not for many inputs (centroidal motion 9 x 16)
   static constexpr size_t kSplitFirstBytes = sizeof(S) * (SplitLayout<M>::inElems(kTile) + SplitLayout<M>::outElems(kTile)) + 256;
-  static constexpr bool kSplitFits = kSplitFirstBytes <= 200 * 1024 && FanSmem<M>::bytes() <= 200 * 1024;
+  static constexpr bool kSplitFits = kSplitFirstBytes <= 200 * 1024 && FanSmem<M, kFanSplitWarps>::bytes() <= 200 * 1024;
 
   /** K0 in the split-role form: same regime as the split line search (a functor with a time-varying input dimension
       keeps the thread-per-instance K0, whose padding rule it shares with the MPC-loop kernel). */
@@ -1131,16 +1131,19 @@ protected:
     record(st); // first candidate done
     if(split)
     {
-      constexpr int ipc = FanSmem<M>::IPC; // listed instances per CTA
-      const size_t smem = FanSmem<M>::bytes();
+      using FS = FanSmem<M, kFanSplitWarps>;
+      constexpr int ipc = FS::IPC; // listed instances per CTA
+      const size_t smem = FS::bytes();
       bool & attr_set = lanes_attr_set_[11];
       if(!attr_set)
       {
-        NMPC_CUDA_CHECK(cudaFuncSetAttribute(forward_fanout_split_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NMPC_CUDA_CHECK(cudaFuncSetAttribute(forward_fanout_split_kernel<M, kFanSplitWarps>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
       }
       const int grid = (B + ipc - 1) / ipc; // worst case: every instance listed
-      launchPdl(forward_fanout_split_kernel<M>, dim3(grid), dim3((2 * kFanWarps + 1) * 32), smem, st, model_, ws_, prm_, fan_, iter);
+      launchPdl(forward_fanout_split_kernel<M, kFanSplitWarps>, dim3(grid), dim3((2 * kFanSplitWarps + 1) * 32), smem, st, model_,
+                ws_, prm_, fan_, iter);
     }
     else
     {

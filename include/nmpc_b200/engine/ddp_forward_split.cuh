@@ -29,6 +29,10 @@ namespace ddp
 constexpr int kSPS = 2; //!< steps per ring stage
 constexpr int kSplitIn = 4; //!< stages of the loader -> rollout ring
 constexpr int kSplitOut = 4; //!< stages of the rollout -> cost ring
+/** Rollout warps (= pairs of listed instances) per CTA of the phase-2 KERNEL.  Measured at B = 4096, M-fixed: 4 warps
+    (rollout and cost warps sharing the four schedulers) 39.0 us, 2 warps 35.8 us, 1 warp 33.8 us per launch: a rollout
+    warp wants a scheduler to itself.  (The persistent tile kernel keeps four: its CTA is one tile's 9 warps.) */
+constexpr int kFanSplitWarps = 1;
 
 template<class M>
 struct SplitLayout
@@ -470,23 +474,23 @@ __global__ void __launch_bounds__(96) rollout_init_split_kernel(const __grid_con
 
 /** Shared-memory carve-up of phase 2: one broadcast in-ring for the CTA's eight listed instances and one out-ring per
     rollout / cost warp pair. */
-template<class M>
+template<class M, int W = kFanWarps>
 struct FanSmem
 {
   using S = typename M::Scalar;
   using SL = SplitLayout<M>;
   static constexpr int IPW = 32 / kFanLanes; //!< listed instances per rollout warp
-  static constexpr int IPC = kFanWarps * IPW; //!< ... per CTA and round
+  static constexpr int IPC = W * IPW; //!< ... per CTA and round
   static constexpr int ROWS = IPC * SL::O::SIZE; //!< in-ring rows of one step: [instance][operand]
   S * in_ring; //!< [kSplitIn][kSPS][ROWS]
-  S * out_ring; //!< [kFanWarps][kSplitOut][kSPS][OUT][32]
+  S * out_ring; //!< [W][kSplitOut][kSPS][OUT][32]
   unsigned long long * in_full;
   unsigned long long * in_empty;
   unsigned long long * out_bars; //!< per pair: kSplitOut full, kSplitOut empty
   static constexpr size_t bytes()
   {
-    return ((sizeof(S) * ((size_t)kSplitIn * kSPS * ROWS + (size_t)kFanWarps * SL::outElems(kTile))
-             + sizeof(unsigned long long) * (2 * kSplitIn + 2 * kSplitOut * kFanWarps) + 127)
+    return ((sizeof(S) * ((size_t)kSplitIn * kSPS * ROWS + (size_t)W * SL::outElems(kTile))
+             + sizeof(unsigned long long) * (2 * kSplitIn + 2 * kSplitOut * W) + 127)
             / 128)
            * 128;
   }
@@ -494,7 +498,7 @@ struct FanSmem
   {
     in_ring = reinterpret_cast<S *>(base);
     out_ring = in_ring + (size_t)kSplitIn * kSPS * ROWS;
-    in_full = reinterpret_cast<unsigned long long *>(out_ring + (size_t)kFanWarps * SL::outElems(kTile));
+    in_full = reinterpret_cast<unsigned long long *>(out_ring + (size_t)W * SL::outElems(kTile));
     in_empty = in_full + kSplitIn;
     out_bars = in_empty + kSplitIn;
   }
@@ -504,9 +508,9 @@ struct FanSmem
     for(int st = 0; st < kSplitIn; st++)
     {
       mbarInit(&in_full[st], 32);
-      mbarInit(&in_empty[st], kFanWarps * 32);
+      mbarInit(&in_empty[st], W * 32);
     }
-    for(int st = 0; st < 2 * kSplitOut * kFanWarps; st++) mbarInit(&out_bars[st], 32);
+    for(int st = 0; st < 2 * kSplitOut * W; st++) mbarInit(&out_bars[st], 32);
   }
   __device__ __forceinline__ S * outCol(int pair, int lane) const
   {
@@ -523,17 +527,17 @@ struct FanSmem
 };
 
 /** One round of phase 2 for the listed instances list[slot0 .. slot0 + IPC) (slots >= count are idle): candidates
-    1 .. n_alpha-1 of each at once, 16 lanes per instance.  Warps 0 .. kFanWarps-1 roll out, warp kFanWarps + w is
-    the cost partner of warp w (same lane = same candidate), warp 2 kFanWarps loads (the operands are read as a
+    1 .. n_alpha-1 of each at once, 16 lanes per instance.  Warps 0 .. W-1 roll out, warp W + w is
+    the cost partner of warp w (same lane = same candidate), warp 2 W loads (the operands are read as a
     broadcast by the lanes of a group).  Candidate trajectories go to the scratch columns (item_slot0 + instance of
     the round) * 16 + candidate; the group then copies its winner into the instance's other buffer.  in_base /
     out_base: ring stages already passed (the rings' mbarriers keep their phase across calls). */
-template<class M>
+template<class M, int W = kFanWarps>
 __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
                                             const Workspace<typename M::Scalar> & ws,
                                             const SolverParams<typename M::Scalar> & prm,
                                             const FwdFanout<typename M::Scalar> & fan,
-                                            const FanSmem<M> & sm,
+                                            const FanSmem<M, W> & sm,
                                             int iter,
                                             const int * list,
                                             int count,
@@ -548,14 +552,14 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
   constexpr int NX = M::NX, NU = M::NU;
   using O = typename SplitLayout<M>::O;
   constexpr int GA = kFanLanes;
-  constexpr int IPW = FanSmem<M>::IPW;
-  constexpr int ROWS = FanSmem<M>::ROWS;
+  constexpr int IPW = FanSmem<M, W>::IPW;
+  constexpr int ROWS = FanSmem<M, W>::ROWS;
   constexpr unsigned kFull = 0xffffffffu;
   constexpr unsigned kGroupMask = (1u << GA) - 1u;
   const size_t Bp = ws.Bp;
   const int N = prm.N;
 
-  if(warp == 2 * kFanWarps)
+  if(warp == 2 * W)
   {
     // loader: lane l streams in-ring rows l, l + 32, ... of every step; row = (instance of the round) * O::SIZE + operand
     constexpr int RPL = (ROWS + 31) / 32;
@@ -619,11 +623,11 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
     }
     return;
   }
-  if(warp > 2 * kFanWarps) return;
+  if(warp > 2 * W) return;
 
   using LM = typename LatencyOf<M>::type;
   const LM model(model_in_constant_bank);
-  const int pair = warp % kFanWarps;
+  const int pair = warp % W;
   const int g = lane / GA;
   const int a = lane % GA;
   const int inst = pair * IPW + g; // instance of the round
@@ -636,7 +640,7 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
   const S my_alpha = prm.alpha_list[work ? (1 + a) : 0];
   S * out_col = sm.outCol(pair, lane);
 
-  if(warp < kFanWarps)
+  if(warp < W)
   {
     Matrix<S, NX, 1> x;
 #pragma unroll
@@ -723,8 +727,10 @@ __device__ __forceinline__ void fanoutRound(const M & model_in_constant_bank,
 }
 
 /** Phase 2 as a kernel of its own: CTA c serves the slots c * IPC .. of the global work list. */
-template<class M>
-__global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
+// 167 registers at W = 1 (the winner copy keeps 40 loads in flight): four CTAs per SM.  Capping the registers for more
+// resident CTAs (6 / 10 per SM) spills and costs more than it gains: 43.0 / 54.1 us vs 33.8 us per launch.
+template<class M, int W>
+__global__ void __launch_bounds__((2 * W + 1) * 32)
     forward_fanout_split_kernel(const __grid_constant__ M model_in_constant_bank,
                                 const __grid_constant__ Workspace<typename M::Scalar> ws,
                                 const __grid_constant__ SolverParams<typename M::Scalar> prm,
@@ -733,17 +739,17 @@ __global__ void __launch_bounds__((2 * kFanWarps + 1) * 32)
 {
   pdlPrologue();
   const int count = *fan.count;
-  const int cta_slot0 = blockIdx.x * FanSmem<M>::IPC;
+  const int cta_slot0 = blockIdx.x * FanSmem<M, W>::IPC;
   if(cta_slot0 >= count) return; // CTA-uniform
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const FanSmem<M> sm(smem_raw);
+  const FanSmem<M, W> sm(smem_raw);
   if(threadIdx.x == 0)
   {
     sm.initBarriers();
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  fanoutRound<M>(model_in_constant_bank, ws, prm, fan, sm, iter, fan.list, count, cta_slot0, (size_t)cta_slot0,
+  fanoutRound<M, W>(model_in_constant_bank, ws, prm, fan, sm, iter, fan.list, count, cta_slot0, (size_t)cta_slot0,
                  threadIdx.x >> 5, threadIdx.x & 31, 0u, 0u);
 }
 } // namespace ddp
