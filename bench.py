@@ -313,6 +313,12 @@ def ddp_roofline(wl, B, value_per_gpu, solver, iter_ms, launches, peak, peak_src
            (("derivative", 0), ("backward", 1), ("forward_first", 2), ("forward_rest", 3))}
     if fused:
         per["derivative"] = 0.0
+    # beyond forward_phased_max_batch the line search is ONE kernel (forward_kernel): the event between the two phases
+    # then only brackets a gap, so the whole line search (time and bytes) is reported under forward_first
+    single_forward = not (solver.get_tuning("forward_lanes") in (-1, 3) and B <= solver.get_tuning("forward_phased_max_batch"))
+    if single_forward:
+        per["forward_first"] += per["forward_rest"]
+        per["forward_rest"] = 0.0
     total_ms = sum(per.values()) or 1.0
     # algorithmic bytes per launch (all B instances of this GPU), averaged over the launches of one solve
     compulsory = {
@@ -321,17 +327,24 @@ def ddp_roofline(wl, B, value_per_gpu, solver, iter_ms, launches, peak, peak_src
         "forward_first": sz * el["D3"] * float(first_passes.sum()) / n_iter_launch,
         "forward_rest": sz * (el["fan_read"] * float(listed.sum()) + el["fan_write"] * float(winners.sum())) / n_iter_launch,
     }
+    if single_forward:
+        compulsory["forward_first"] += compulsory["forward_rest"]
+        compulsory["forward_rest"] = 0.0
     survey = {
         "derivative": compulsory["derivative"],
         "backward": sz * ((el["D1"] + el["D2"]) if fused else el["D2"]) * float(n_bwd.sum()) / n_iter_launch,
         "forward_first": compulsory["forward_first"],
         "forward_rest": sz * el["D3"] * float((n_fwd - first_passes).sum()) / n_iter_launch,
     }
+    if single_forward:
+        survey["forward_first"] += survey["forward_rest"]
+        survey["forward_rest"] = 0.0
     names = {
         "derivative": "ddp::linearize_kernel",
         "backward": "ddp::backward_lanes_kernel / backward_fused_kernel (K1 + K2 in one kernel: producer warps linearise, "
                     "consumer warps sweep)" if fused else "ddp::backward_kernel",
-        "forward_first": "ddp::forward_first_split_kernel / forward_first_kernel (alpha_list[0] of every instance)",
+        "forward_first": "ddp::forward_kernel (the whole line search in one kernel)" if single_forward else
+                         "ddp::forward_first_split_kernel / forward_first_kernel (alpha_list[0] of every instance)",
         "forward_rest": "ddp::forward_fanout_split_kernel / forward_fanout_kernel (other candidates of the listed instances)",
     }
     kernels = {}
