@@ -304,7 +304,9 @@ protected:
     nmpc_b200::throwOnError(nmpc_b200_ddp_set_input_limits_horizon(handle_, N, lo.data(), hi.data()));
   }
 
-  nmpc_b200_ddp_config cConfig() const
+public:
+  /** The C-ABI form of a Configuration (also used by ShardedDDPSolver). */
+  static nmpc_b200_ddp_config toC(const Configuration & config_)
   {
     nmpc_b200_ddp_config c;
     nmpc_b200_ddp_config_default(&c);
@@ -326,6 +328,12 @@ protected:
     c.cost_update_ratio_thre = config_.cost_update_ratio_thre;
     c.cost_update_thre = config_.cost_update_thre;
     return c;
+  }
+
+protected:
+  nmpc_b200_ddp_config cConfig() const
+  {
+    return toC(config_);
   }
 
   void ensureHandle()

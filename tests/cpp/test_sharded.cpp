@@ -10,6 +10,8 @@
 #include <cuda_runtime_api.h>
 
 #include <nmpc_b200/c_api.h>
+#include <nmpc_b200/models/cartpole.h>
+#include <nmpc_ddp/ShardedDDPSolver.h>
 
 #define CHECK(call)                                                            \
   do                                                                           \
@@ -112,6 +114,23 @@ int main()
   rc = nmpc_b200_ddp_sharded_get(sh, NMPC_B200_DDP_COST, c3.data(), 8, -1);
   std::printf("short_dst %d\n", rc);
   CHECK(nmpc_b200_ddp_sharded_destroy(sh));
+
+  // the same through the C++ facade (include/nmpc_ddp/ShardedDDPSolver.h)
+  {
+    using Problem = nmpc_ddp::FunctorProblem<nmpc_b200::models::CartPole<double>>;
+    auto problem = std::make_shared<Problem>("cartpole");
+    nmpc_ddp::ShardedDDPSolver<4, 1> solver(problem, B, {devices[0], devices[1]});
+    solver.config().horizon_steps = N;
+    solver.config().max_iter = 12;
+    const std::vector<bool> converged = solver.solveBatch(B, 0.0, x0.data(), u_init.data(), N);
+    const auto u0 = solver.firstInputs();
+    bool same = (int)u0.size() == B && solver.numShards() == 2;
+    for(int b = 0; b < B && same; b++) same = u0[b][0] == u0_one[b];
+    std::printf("facade_identical %d\n", (int)same);
+    int n_conv = 0;
+    for(int b = 0; b < B; b++) n_conv += converged[b] ? 1 : 0;
+    std::printf("facade_converged %d\n", n_conv);
+  }
   CHECK(nmpc_b200_ddp_destroy(one));
   std::printf("done 1\n");
   return 0;

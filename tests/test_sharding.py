@@ -113,7 +113,8 @@ def test_sharded_cpp_caller_world2(sharded_bin, gpu):
     assert d["done"] == "1" and d["num_shards"] == "2"
     assert d["range0"].split()[:2] == ["0", "19"] and d["range1"].split()[:2] == ["19", "37"]
     assert float(d["u_max_rel_diff"]) <= 1e-9
-    for key in ("u_identical", "cost_identical", "iters_identical", "u0_peer_identical", "small_identical"):
+    for key in ("u_identical", "cost_identical", "iters_identical", "u0_peer_identical", "small_identical",
+                "facade_identical"):
         assert d[key] == "1", (key, r.stdout)
     assert int(d["max_iters"]) >= 3
     assert d["too_large"] != "0" and d["short_dst"] != "0"
