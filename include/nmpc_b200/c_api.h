@@ -418,6 +418,32 @@ extern "C"
       backward, forward, update}. */
   int nmpc_b200_fmpc_get_durations(nmpc_b200_fmpc * h, double * ms, int * launches);
 
+  /** nmpc_b200_ddp_create_sharded ("several GPUs, one box") for FmpcSolver: x0[B][NX] and the five Variable arrays as in nmpc_b200_fmpc_solve, all host memory; fields
+      as in nmpc_b200_fmpc_field. */
+  typedef struct nmpc_b200_fmpc_sharded nmpc_b200_fmpc_sharded;
+  int nmpc_b200_fmpc_create_sharded(const char * model,
+                                    const double * params,
+                                    int n_params,
+                                    const nmpc_b200_fmpc_config * cfg,
+                                    int total_capacity,
+                                    const int * devices,
+                                    int n_devices,
+                                    nmpc_b200_fmpc_sharded ** out);
+  int nmpc_b200_fmpc_sharded_destroy(nmpc_b200_fmpc_sharded * h);
+  int nmpc_b200_fmpc_sharded_num_shards(const nmpc_b200_fmpc_sharded * h);
+  int nmpc_b200_fmpc_sharded_set_config(nmpc_b200_fmpc_sharded * h, const nmpc_b200_fmpc_config * cfg);
+  int nmpc_b200_fmpc_sharded_solve(nmpc_b200_fmpc_sharded * h,
+                                   int B,
+                                   double current_t,
+                                   const double * x0,
+                                   const double * x,
+                                   const double * u,
+                                   const double * lambda,
+                                   const double * s,
+                                   const double * nu,
+                                   int n_steps);
+  int nmpc_b200_fmpc_sharded_get(nmpc_b200_fmpc_sharded * h, int what, void * dst, size_t dst_bytes, int dst_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,8 @@ EXPORTED_SYMBOLS = [
     "nmpc_b200_ddp_create_sharded", "nmpc_b200_ddp_sharded_destroy", "nmpc_b200_ddp_sharded_num_shards",
     "nmpc_b200_ddp_sharded_shard", "nmpc_b200_ddp_sharded_range", "nmpc_b200_ddp_sharded_set_config",
     "nmpc_b200_ddp_sharded_set_input_limits", "nmpc_b200_ddp_sharded_solve", "nmpc_b200_ddp_sharded_get",
+    "nmpc_b200_fmpc_create_sharded", "nmpc_b200_fmpc_sharded_destroy", "nmpc_b200_fmpc_sharded_num_shards",
+    "nmpc_b200_fmpc_sharded_set_config", "nmpc_b200_fmpc_sharded_solve", "nmpc_b200_fmpc_sharded_get",
     "nmpc_b200_peer_buffer_create", "nmpc_b200_peer_buffer_open", "nmpc_b200_peer_buffer_close",
     "nmpc_b200_peer_buffer_destroy", "nmpc_b200_peer_signal", "nmpc_b200_peer_wait", "nmpc_b200_peer_check",
 ]
@@ -151,6 +153,13 @@ def lib():
         L.nmpc_b200_ddp_sharded_set_input_limits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.nmpc_b200_ddp_sharded_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
         L.nmpc_b200_ddp_sharded_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+        L.nmpc_b200_fmpc_create_sharded.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                    C.c_int, C.c_void_p]
+        L.nmpc_b200_fmpc_sharded_destroy.argtypes = [C.c_void_p]
+        L.nmpc_b200_fmpc_sharded_num_shards.argtypes = [C.c_void_p]
+        L.nmpc_b200_fmpc_sharded_set_config.argtypes = [C.c_void_p, C.c_void_p]
+        L.nmpc_b200_fmpc_sharded_solve.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 6 + [C.c_int]
+        L.nmpc_b200_fmpc_sharded_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         L.nmpc_b200_peer_buffer_create.argtypes = [C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
         L.nmpc_b200_peer_buffer_open.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.nmpc_b200_peer_buffer_close.argtypes = [C.c_void_p, C.c_int]

@@ -117,6 +117,77 @@ struct Shard
   std::unique_ptr<Worker> worker;
 };
 
+struct FmpcShard
+{
+  int device = 0;
+  nmpc_b200_fmpc * handle = nullptr;
+  std::unique_ptr<Worker> worker;
+};
+
+/** Runs job(shard index) on every shard's worker and waits for all; the first failure is rethrown. */
+template<class ShardVector>
+void forAllShards(ShardVector & shards, const std::function<void(int)> & job)
+{
+  for(size_t i = 0; i < shards.size(); i++) shards[i].worker->post([&job, i] { job((int)i); });
+  int code = NMPC_B200_OK;
+  std::string msg;
+  for(size_t i = 0; i < shards.size(); i++)
+  {
+    std::string m;
+    const int c = shards[i].worker->wait(m);
+    if(c != NMPC_B200_OK && code == NMPC_B200_OK)
+    {
+      code = c;
+      msg = "shard " + std::to_string(i) + " (device " + std::to_string(shards[i].device) + "): " + m;
+    }
+  }
+  if(code != NMPC_B200_OK) throw Error(code, msg);
+}
+
+/** Peer access from `from` to `to` for direct stores (idempotent). */
+void enablePeerStores(int from, int to)
+{
+  if(from == to) return;
+  DeviceGuard guard(from);
+  int can = 0;
+  NMPC_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, from, to));
+  if(!can)
+    throw Error(NMPC_B200_ERR_UNSUPPORTED,
+                "device " + std::to_string(from) + " cannot store into device " + std::to_string(to) + " (no peer access)");
+  const cudaError_t err = cudaDeviceEnablePeerAccess(to, 0);
+  if(err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) NMPC_CUDA_CHECK(err);
+  cudaGetLastError();
+}
+
+/** Bytes of one instance's row of field `what` (nmpc_b200_fmpc_field). */
+size_t fmpcFieldRowBytes(int what, int nx, int nu, int ng, const nmpc_b200_fmpc_config & c)
+{
+  const size_t N = c.horizon_steps;
+  switch(what)
+  {
+    case NMPC_B200_FMPC_X:
+    case NMPC_B200_FMPC_LAMBDA:
+      return sizeof(double) * (N + 1) * nx;
+    case NMPC_B200_FMPC_U:
+    case NMPC_B200_FMPC_K_FF:
+      return sizeof(double) * N * nu;
+    case NMPC_B200_FMPC_S:
+    case NMPC_B200_FMPC_NU:
+      return sizeof(double) * N * ng;
+    case NMPC_B200_FMPC_K_FB:
+      return sizeof(double) * N * nu * nx;
+    case NMPC_B200_FMPC_TRACE:
+      return sizeof(double) * (size_t)c.max_iter * 5;
+    case NMPC_B200_FMPC_U0:
+      return sizeof(double) * nu;
+    case NMPC_B200_FMPC_STATUS:
+    case NMPC_B200_FMPC_N_TRACE:
+      return sizeof(int);
+    default:
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "unknown field " + std::to_string(what));
+  }
+}
+
 void shardRange(int B, int n, int s, int & begin, int & end)
 {
   const int base = B / n, rem = B % n;
@@ -412,6 +483,146 @@ int nmpc_b200_ddp_sharded_get(nmpc_b200_ddp_sharded * h, int what, void * dst, s
       check(nmpc_b200_ddp_get(sh.handle, what, static_cast<char *>(dst) + row * b, row * (e - b), dst_device >= 0 ? 1 : 0,
                               nullptr));
       check(nmpc_b200_ddp_sync(sh.handle));
+    });
+  });
+}
+
+/* --------------------------------------------------------------------------------- FMPC ---- */
+} // extern "C"
+
+struct nmpc_b200_fmpc_sharded
+{
+  std::vector<FmpcShard> shards;
+  int nx = 0, nu = 0, ng = 0, capacity = 0, last_B = 0;
+  nmpc_b200_fmpc_config cfg;
+
+  ~nmpc_b200_fmpc_sharded()
+  {
+    for(auto & s : shards)
+    {
+      s.worker.reset();
+      if(s.handle) nmpc_b200_fmpc_destroy(s.handle);
+    }
+  }
+};
+
+extern "C"
+{
+int nmpc_b200_fmpc_create_sharded(const char * model,
+                                  const double * params,
+                                  int n_params,
+                                  const nmpc_b200_fmpc_config * cfg,
+                                  int total_capacity,
+                                  const int * devices,
+                                  int n_devices,
+                                  nmpc_b200_fmpc_sharded ** out)
+{
+  return guarded([&] {
+    if(out == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null output handle");
+    *out = nullptr;
+    if(total_capacity <= 0) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "total_capacity must be positive");
+    const int visible = nmpc_b200_device_count();
+    if(visible <= 0) throw Error(NMPC_B200_ERR_NO_DEVICE, "no usable CUDA device; nmpc_b200 has no CPU fallback");
+    if(n_devices <= 0)
+    {
+      n_devices = visible;
+      devices = nullptr;
+    }
+    auto h = std::make_unique<nmpc_b200_fmpc_sharded>();
+    int np = 0;
+    check(nmpc_b200_model_dims(model, &h->nx, &h->nu, &h->ng, &np));
+    if(cfg)
+      h->cfg = *cfg;
+    else
+      nmpc_b200_fmpc_config_default(&h->cfg);
+    h->capacity = total_capacity;
+    const int per_shard = (total_capacity + n_devices - 1) / n_devices;
+    h->shards.resize(n_devices);
+    for(int s = 0; s < n_devices; s++)
+    {
+      FmpcShard & sh = h->shards[s];
+      sh.device = devices ? devices[s] : s;
+      check(nmpc_b200_fmpc_create(model, params, n_params, &h->cfg, per_shard, sh.device, &sh.handle));
+      sh.worker = std::make_unique<Worker>();
+    }
+    *out = h.release();
+  });
+}
+
+int nmpc_b200_fmpc_sharded_destroy(nmpc_b200_fmpc_sharded * h)
+{
+  return guarded([&] { delete h; });
+}
+
+int nmpc_b200_fmpc_sharded_num_shards(const nmpc_b200_fmpc_sharded * h)
+{
+  return h ? (int)h->shards.size() : 0;
+}
+
+int nmpc_b200_fmpc_sharded_set_config(nmpc_b200_fmpc_sharded * h, const nmpc_b200_fmpc_config * cfg)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_SHARDED(h);
+    if(cfg == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null config");
+    for(auto & s : h->shards) check(nmpc_b200_fmpc_set_config(s.handle, cfg));
+    h->cfg = *cfg;
+  });
+}
+
+int nmpc_b200_fmpc_sharded_solve(nmpc_b200_fmpc_sharded * h,
+                                 int B,
+                                 double current_t,
+                                 const double * x0,
+                                 const double * x,
+                                 const double * u,
+                                 const double * lambda,
+                                 const double * s,
+                                 const double * nu,
+                                 int n_steps)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_SHARDED(h);
+    if(B <= 0 || B > h->capacity)
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT,
+                  "batch size " + std::to_string(B) + " outside (0, " + std::to_string(h->capacity) + "]");
+    if(!x0 || !x || !u || !lambda || !s || !nu) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null input array");
+    const int n = (int)h->shards.size();
+    const size_t N = n_steps > 0 ? n_steps : 0;
+    const size_t r_x0 = h->nx, r_x = (N + 1) * h->nx, r_u = N * h->nu, r_g = N * h->ng;
+    h->last_B = 0;
+    forAllShards(h->shards, [&](int i) {
+      int b = 0, e = 0;
+      shardRange(B, n, i, b, e);
+      if(e == b) return;
+      FmpcShard & sh = h->shards[i];
+      check(nmpc_b200_fmpc_solve(sh.handle, e - b, current_t, x0 + b * r_x0, x + b * r_x, u + b * r_u, lambda + b * r_x,
+                                 s + b * r_g, nu + b * r_g, n_steps, 0, nullptr));
+      check(nmpc_b200_fmpc_sync(sh.handle));
+    });
+    h->last_B = B;
+  });
+}
+
+int nmpc_b200_fmpc_sharded_get(nmpc_b200_fmpc_sharded * h, int what, void * dst, size_t dst_bytes, int dst_device)
+{
+  return guarded([&] {
+    NMPC_REQUIRE_SHARDED(h);
+    if(h->last_B <= 0) throw Error(NMPC_B200_ERR_RUNTIME, "get() before solve()");
+    if(dst == nullptr) throw Error(NMPC_B200_ERR_INVALID_ARGUMENT, "null destination");
+    const size_t row = fmpcFieldRowBytes(what, h->nx, h->nu, h->ng, h->cfg);
+    const int B = h->last_B, n = (int)h->shards.size();
+    if(dst_bytes < row * B)
+      throw Error(NMPC_B200_ERR_INVALID_ARGUMENT,
+                  "destination holds " + std::to_string(dst_bytes) + " bytes, the field needs " + std::to_string(row * B));
+    forAllShards(h->shards, [&](int i) {
+      int b = 0, e = 0;
+      shardRange(B, n, i, b, e);
+      if(e == b) return;
+      FmpcShard & sh = h->shards[i];
+      if(dst_device >= 0) enablePeerStores(sh.device, dst_device);
+      check(nmpc_b200_fmpc_get(sh.handle, what, static_cast<char *>(dst) + row * b, row * (e - b), dst_device >= 0 ? 1 : 0,
+                               nullptr));
+      check(nmpc_b200_fmpc_sync(sh.handle));
     });
   });
 }

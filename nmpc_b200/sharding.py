@@ -225,3 +225,62 @@ class PeerBuffer:
             else:
                 lib().nmpc_b200_peer_buffer_close(self._ptr, self.device)
             self._ptr = C.c_void_p()
+
+
+class ShardedFmpcSolver:
+    """A batch of FmpcSolver objects sharded over several GPUs from one process (nmpc_b200_fmpc_create_sharded)."""
+
+    def __init__(self, problem, params=None, total_capacity=1, devices=None, config=None):
+        from .fmpc import FmpcConfiguration
+
+        self._h = C.c_void_p()
+        self.nx, self.nu, self.ng, self.n_params = _capi.model_dims(problem)
+        self.params = (_capi.model_default_params(problem) if params is None else np.ascontiguousarray(
+            params, dtype=np.float64))
+        self._config = config if config is not None else FmpcConfiguration()
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        st = self._config.to_struct()
+        check(lib().nmpc_b200_fmpc_create_sharded(problem.encode(), self.params.ctypes.data_as(C.c_void_p),
+                                                  int(self.params.size), C.byref(st), int(total_capacity),
+                                                  None if dev is None else dev.ctypes.data_as(C.c_void_p),
+                                                  0 if dev is None else int(dev.size), C.byref(self._h)))
+        self._applied = bytes(st)
+        self._B = 0
+
+    def config(self):
+        return self._config
+
+    def num_shards(self):
+        return lib().nmpc_b200_fmpc_sharded_num_shards(self._h)
+
+    def solve_batch(self, current_t, x0, var):
+        """FmpcSolver::solve for every instance: x0 [B, NX] and a fmpc.Variable of host arrays.  Returns the status words."""
+        st = self._config.to_struct()
+        if bytes(st) != self._applied:
+            check(lib().nmpc_b200_fmpc_sharded_set_config(self._h, C.byref(st)))
+            self._applied = bytes(st)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        B = x0.shape[0]
+        arrs = [np.ascontiguousarray(getattr(var, n), dtype=np.float64)
+                for n in ("x_list", "u_list", "lambda_list", "s_list", "nu_list")]
+        n_steps = int(arrs[1].shape[1])
+        check(lib().nmpc_b200_fmpc_sharded_solve(self._h, B, float(current_t), x0.ctypes.data_as(C.c_void_p),
+                                                 *[a.ctypes.data_as(C.c_void_p) for a in arrs], n_steps))
+        self._B = B
+        return self.get(8, (B,), np.int32)
+
+    def get(self, what, shape, dtype=np.float64):
+        out = np.zeros(shape, dtype=dtype)
+        check(lib().nmpc_b200_fmpc_sharded_get(self._h, int(what), out.ctypes.data_as(C.c_void_p), out.nbytes, -1))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().nmpc_b200_fmpc_sharded_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover
+            pass

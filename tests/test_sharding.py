@@ -214,3 +214,34 @@ def test_peer_buffer_gather_between_two_processes(gpu):
             want = np.concatenate([ret[f"local{r}_step{step}"] for r in range(world)])
             assert np.array_equal(ret[f"u0_step{step}"], want)
         assert ret["timeout_reported"] is True
+
+
+@pytest.mark.gpu
+def test_sharded_fmpc_matches_one_handle(gpu):
+    """nmpc_b200_fmpc_create_sharded: a ragged FMPC batch over two shards == the same batch on one handle, bit for bit."""
+    from nmpc_b200.sharding import ShardedFmpcSolver
+
+    n_dev = gpu.device_count()
+    devices = [0, 1] if n_dev > 1 else [0, 0]
+    B, N = 21, 30
+    x0 = O.cartpole_x0(B, 8)
+    one = gpu.FmpcSolver("cartpole", batch_capacity=B)
+    one.config().horizon_steps, one.config().max_iter = N, 4
+    v = one.make_variable(B)
+    v.reset(0.0, 0.0, 0.0, 1.0, 1.0)
+    status_one = np.asarray(one.solve_batch(0.0, x0, v))
+    out = one.variable()
+    sh = ShardedFmpcSolver("cartpole", total_capacity=B, devices=devices)
+    sh.config().horizon_steps, sh.config().max_iter = N, 4
+    w = one.make_variable(B)
+    w.reset(0.0, 0.0, 0.0, 1.0, 1.0)
+    status = sh.solve_batch(0.0, x0, w)
+    assert sh.num_shards() == 2 and np.array_equal(status, status_one.astype(np.int32))
+    assert np.array_equal(sh.get(1, (B, N, 1)), out.u_list)
+    assert np.array_equal(sh.get(0, (B, N + 1, 4)), out.x_list)
+    assert np.array_equal(sh.get(4, (B, N, 4)), out.nu_list)
+    assert np.array_equal(sh.get(10, (B, 1)), out.u_list[:, 0, :])
+    with pytest.raises(gpu.NmpcB200Error):
+        sh.solve_batch(0.0, O.cartpole_x0(B + 1, 1), one.make_variable(B + 1))
+    sh.close()
+    one.close()
