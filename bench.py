@@ -12,8 +12,10 @@
   --total-batch B     configs[4] (strong scaling): B instances split over the --gpus ranks instead of --batch per GPU
 
 A "step" is one batched solve() of the workload's instances.  One process per GPU (torchrun sets RANK / LOCAL_RANK /
-WORLD_SIZE); the batch shards with no data-path collective; the only collective is the optional NCCL all-gather of the
-first-step controls after each solve.  Rank 0 prints ONE JSON line; DESIGN.md section 5 defines every field.
+WORLD_SIZE); the batch shards with no data-path collective; the only exchange is the gather of the first-step
+controls on rank 0 after each solve -- by default one-sided: every rank's gather kernel stores its rows into rank 0's
+buffer over NVLink and raises a flag word (--gather peer; --gather nccl is the all-gather, --no-gather none).  Rank 0
+prints ONE JSON line; DESIGN.md section 5 defines every field.
 """
 import argparse
 import json

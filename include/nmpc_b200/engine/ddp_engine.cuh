@@ -891,7 +891,7 @@ protected:
   }
 
   /** K1 + K2 fused (producer warp + consumer warp per 32-instance tile, ddp_backward_fused.cuh): the default while the
-      thread-per-instance sweep is the K2 variant in use, i.e. for n_x < 8.  NMPC_B200_BWD_FUSED=0 restores the
+      thread-per-instance sweep is the K2 variant in use, i.e. for n_x < 8.  The knob backward_fused = 0 restores the
       three-kernel pipeline. */
   bool backwardUsesFused(int B) const
   {
@@ -990,7 +990,7 @@ protected:
 
   /** K2 variant for many inputs (n_u >= 8, no input limits): the n_u side spread over the lanes of a group
       (ddp_backward_wide.cuh).  Measured on B200, centroidal motion 9 x 16, B = 1024, one sweep: see DESIGN.md;
-      NMPC_B200_BWD_WIDE=0 falls back to the cooperative variant that recomputes the n_u x n_u part in every lane. */
+      the knob backward_wide = 0 falls back to the cooperative variant that recomputes the n_u x n_u part in every lane. */
   static constexpr int kWideGS = (NU <= 16 && NX < 16) ? 16 : 32;
   static constexpr bool kWideOk = NU >= 8 && NU <= kWideGS && NX < kWideGS;
   bool backwardUsesWide() const

@@ -228,7 +228,7 @@ def test_device_mpc_loop(gpu):
 @pytest.mark.parametrize("reg_type", [1, 2])
 def test_device_wide_sweep_agrees_with_the_cooperative_sweep_and_the_oracle(gpu, reg_type, monkeypatch):
     """K2 for many inputs (ddp_backward_wide.cuh, the default at n_u = 16) against the cooperative variant
-    (NMPC_B200_BWD_WIDE=0) and the oracle, both regularisation types, a ragged batch (odd number of instances: the
+    (knob backward_wide = 0, here through its environment preset NMPC_B200_BWD_WIDE) and the oracle, both regularisation types, a ragged batch (odd number of instances: the
     second half of the last warp idles)."""
     p = O.default_params("centroidal_motion")
     B = 7
