@@ -25,8 +25,14 @@ _lib = None
 
 
 def lib():
+    """oracle/_ref/libnmpc_ref.so (reference headers + Eigen shim); NMPC_REF_EIGEN_LIB selects a build of the same sources
+    against a real Eigen instead (oracle/ref/Makefile target `eigen`)."""
     global _lib
     if _lib is None:
+        override = os.environ.get("NMPC_REF_EIGEN_LIB")
+        if override:
+            _lib = C.CDLL(override)
+            return _lib
         if not available():
             raise RuntimeError("the reference checkout is not present on this machine")
         subprocess.run(["make", "-s", "-C", _REF_DIR, f"REF={REFERENCE_ROOT}"], check=True)

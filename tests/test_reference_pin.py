@@ -106,6 +106,35 @@ def test_golden_file_is_what_the_reference_code_produces():
     assert bytes(a) == bytes(b)
 
 
+@pytest.mark.skipif(not os.environ.get("NMPC_REF_EIGEN_LIB"),
+                    reason="needs the reference headers built against a REAL Eigen (make -C oracle/ref eigen EIGEN_DIR=...; "
+                           "NMPC_REF_EIGEN_LIB=<the .so>): not available in this image")
+def test_golden_vectors_against_a_real_eigen_build():
+    """Where Eigen exists: the committed vectors (reference control flow on the Eigen shim) against the same reference
+    code on real Eigen.  Tolerances are the ones the oracle and the CUDA path are held to, not bit-exactness: Eigen's
+    packet reductions and blocked products round differently from the shim's k-ascending sums."""
+    p = O.default_params("cartpole")
+    for name in ("ddp_ref", "ddp_box200", "ddp_reg2"):
+        cfg = R.ddp_config(**_ddp_cfg(name))
+        lo, hi = _limits(name)
+        for i, x0 in enumerate(GOLDEN[f"{name}/x0"]):
+            o = R.ddp_solve_cartpole(p, cfg, x0, np.zeros(cfg.horizon_steps), u_lo=lo, u_hi=hi)
+            assert o["n_trace"] == GOLDEN[f"{name}/n_trace"][i]
+            assert _rel(o["u"][None], GOLDEN[f"{name}/u"][i][None]).max() <= 1e-9
+            np.testing.assert_allclose(o["trace"][:, 1], GOLDEN[f"{name}/trace"][i][:, 1], rtol=1e-9)
+    for name, model in (("fmpc_cartpole", "fmpc_cartpole"), ("fmpc_oscillator", "fmpc_oscillator")):
+        nx, nu, ng, _ = O.model_dims(model)
+        N, max_iter = int(GOLDEN[f"{name}/N"]), int(GOLDEN[f"{name}/max_iter"])
+        var = {"x": np.zeros((N + 1, nx)), "u": np.zeros((N, nu)), "lambda": np.zeros((N + 1, nx)), "s": np.ones((N, ng)),
+               "nu": np.ones((N, ng))}
+        cfg = O.fmpc_config(horizon_steps=N, max_iter=max_iter)
+        for i, x0 in enumerate(GOLDEN[f"{name}/x0"]):
+            o = R.fmpc_solve(model, O.default_params(model), cfg, x0, var)
+            assert o["status"] == GOLDEN[f"{name}/status"][i]
+            for key in ("x", "u", "lambda", "s", "nu"):
+                assert _rel(o[key][None], GOLDEN[f"{name}/{key}"][i][None]).max() <= 1e-8, (name, key)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", DDP_CASES)
 def test_cuda_matches_reference_ddp(gpu, name):
